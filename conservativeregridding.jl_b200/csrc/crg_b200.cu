@@ -1,0 +1,882 @@
+// crg_b200.cu -- C ABI (include/crg_b200.h) and host orchestration of the B200 engine.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdlib>
+#include <new>
+#include <vector>
+
+#include "broadphase.cuh"
+#include "common.cuh"
+#include "geom.cuh"
+#include "kernels.cuh"
+#include "scan.cuh"
+#include "sort.cuh"
+
+namespace crg {
+thread_local char g_err[512] = "";
+
+int set_error(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    int set(int dev) {
+        CRG_CUDA(cudaGetDevice(&prev));
+        if (dev >= 0 && dev != prev) CRG_CUDA(cudaSetDevice(dev));
+        return CRG_OK;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// One CSR matrix on the device.
+struct Csr {
+    int64_t n_rows = 0, n_cols = 0, nnz = 0;
+    DevBuf<int32_t> rowptr, colidx;
+    DevBuf<double> vals;
+};
+}  // namespace crg
+
+using namespace crg;
+
+struct crg_regridder {
+    crg_options opts;
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    int64_t n_dst = 0, n_src = 0, nnz = 0;
+    Csr A;    // rows = dst, cols = src
+    Csr At;   // rows = src, cols = dst  (== the reference's CSC of A)
+    bool has_At = false;
+    DevBuf<double> dst_areas, src_areas;
+    DevBuf<double> scratch_max;
+    DevBuf<int2> cand_pairs;
+    int64_t n_cand_kept = 0;
+    crg_build_stats stats;
+    // staging for host-pointer applies
+    DevBuf<double> stage_src, stage_dst;
+};
+
+namespace crg {
+
+static int check_device_available() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return set_error(CRG_ERR_NO_DEVICE, "no CUDA device available (%s); libcrgb200 has no CPU fallback",
+                         e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    return CRG_OK;
+}
+
+static int validate_cells(const crg_cells *c, const char *name) {
+    if (!c || !c->verts) return set_error(CRG_ERR_INVALID, "%s: null cells/verts", name);
+    if (c->ncells < 0 || c->ncells >= ((int64_t)1 << 31))
+        return set_error(CRG_ERR_INVALID, "%s: ncells=%lld out of range", name, (long long)c->ncells);
+    if (!c->offsets && (c->nv < 3 || c->nv > CRG_MAX_VERTS))
+        return set_error(CRG_ERR_UNSUPPORTED, "%s: nv=%d outside [3, %d]", name, c->nv, CRG_MAX_VERTS);
+    return CRG_OK;
+}
+
+// A grid staged on the device.
+struct DevCells {
+    DevBuf<double> verts_own;
+    DevBuf<int32_t> off_own;
+    DevBuf<uint8_t> flip;
+    DevBuf<float> diam;
+    CellsView view{};
+    int64_t total_verts = 0;
+};
+
+__global__ void __launch_bounds__(256) check_offsets_kernel(const int32_t *off, int64_t n, int maxv, int *bad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int k = off[i + 1] - off[i];
+        if (k < 3 || k > maxv) atomicExch(bad, 1);
+    }
+}
+
+static int stage_cells(const crg_cells *c, int dim, cudaStream_t st, DevCells *out, const char *name) {
+    const int64_t n = c->ncells;
+    out->view.ncells = n;
+    out->view.nv = c->nv;
+    out->view.flip = nullptr;
+    if (c->offsets) {
+        int32_t last = 0;
+        const int32_t *doff;
+        if (is_device_ptr(c->offsets)) {
+            doff = c->offsets;
+            CRG_CUDA(cudaMemcpyAsync(&last, c->offsets + n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            CRG_CUDA(cudaStreamSynchronize(st));
+        } else {
+            last = c->offsets[n];
+            CRG_TRY(out->off_own.alloc((size_t)n + 1, st));
+            CRG_CUDA(cudaMemcpyAsync(out->off_own.p, c->offsets, sizeof(int32_t) * (size_t)(n + 1),
+                                     cudaMemcpyHostToDevice, st));
+            doff = out->off_own.p;
+        }
+        out->view.off = doff;
+        out->total_verts = last;
+        if (n > 0) {
+            DevBuf<int> bad;
+            CRG_TRY(bad.alloc(1, st));
+            CRG_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
+            check_offsets_kernel<<<ceil_div(n, 256), 256, 0, st>>>(doff, n, CRG_MAX_VERTS, bad.p);
+            CRG_LAUNCH_CHECK();
+            int hb = 0;
+            CRG_CUDA(cudaMemcpyAsync(&hb, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CRG_CUDA(cudaStreamSynchronize(st));
+            if (hb) return set_error(CRG_ERR_UNSUPPORTED, "%s: a cell has fewer than 3 or more than %d vertices", name, CRG_MAX_VERTS);
+        }
+    } else {
+        out->view.off = nullptr;
+        out->total_verts = n * c->nv;
+    }
+    if (is_device_ptr(c->verts)) {
+        out->view.verts = c->verts;
+    } else {
+        CRG_TRY(out->verts_own.alloc((size_t)out->total_verts * dim, st));
+        CRG_CUDA(cudaMemcpyAsync(out->verts_own.p, c->verts, sizeof(double) * (size_t)out->total_verts * dim,
+                                 cudaMemcpyHostToDevice, st));
+        out->view.verts = out->verts_own.p;
+    }
+    return CRG_OK;
+}
+
+struct Timer {
+    std::vector<cudaEvent_t> ev;
+    cudaStream_t st;
+    explicit Timer(cudaStream_t s) : st(s) {}
+    ~Timer() { for (auto e : ev) cudaEventDestroy(e); }
+    int mark() {
+        cudaEvent_t e;
+        CRG_CUDA(cudaEventCreate(&e));
+        CRG_CUDA(cudaEventRecord(e, st));
+        ev.push_back(e);
+        return CRG_OK;
+    }
+    double ms(int a, int b) {
+        float f = 0.f;
+        if (cudaEventElapsedTime(&f, ev[a], ev[b]) != cudaSuccess) { cudaGetLastError(); return 0.0; }
+        return f;
+    }
+};
+
+// Sort COO (keys = row<<32|col, f64 values) -> CSR; optionally also the transposed CSR.
+// keys/vals buffers have capacity `cap` (>= n) and are consumed.
+static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &valA, int64_t n, bool row_sorted_hint,
+                    Timer &tm, int *t_sort_csr0, int *t_sort_csr1, int *t_sort_csc1) {
+    cudaStream_t st = R->stream;
+    const int bits_src = ilog2_ceil((uint64_t)(R->n_src > 1 ? R->n_src : 2));
+    const int bits_dst = ilog2_ceil((uint64_t)(R->n_dst > 1 ? R->n_dst : 2));
+    (void)row_sorted_hint;
+    DevBuf<uint64_t> keyB;
+    DevBuf<double> valB;
+    CRG_TRY(keyB.alloc((size_t)(n > 0 ? n : 1), st));
+    CRG_TRY(valB.alloc((size_t)(n > 0 ? n : 1), st));
+    *t_sort_csr0 = (int)tm.ev.size();
+    CRG_TRY(tm.mark());
+    uint64_t *ka = keyA.p, *kb = keyB.p;
+    uint64_t *va = (uint64_t *)valA.p, *vb = (uint64_t *)valB.p;
+    bool inb = false;
+    int p1 = 0, p2 = 0;
+    // LSD: low word (src) digits first, then the high word (dst) digits
+    CRG_TRY(radix_sort_pairs(ka, va, kb, vb, n, 0, bits_src, &inb, &p1, st));
+    if (inb) { std::swap(ka, kb); std::swap(va, vb); }
+    CRG_TRY(radix_sort_pairs(ka, va, kb, vb, n, 32, 32 + bits_dst, &inb, &p2, st));
+    if (inb) { std::swap(ka, kb); std::swap(va, vb); }
+    R->stats.sort_passes_csr = p1 + p2;
+    // duplicate summation (segmented reduce over equal keys)
+    int64_t nnz = n;
+    if (n > 0) {
+        DevBuf<uint32_t> flags, pos;
+        CRG_TRY(flags.alloc((size_t)n, st));
+        CRG_TRY(pos.alloc((size_t)n + 1, st));
+        mark_heads_kernel<<<ceil_div(n, 256), 256, 0, st>>>(ka, n, flags.p);
+        CRG_LAUNCH_CHECK();
+        CRG_TRY((exclusive_scan<uint32_t, uint32_t>(flags.p, n, pos.p, st)));
+        uint32_t nu = 0;
+        CRG_CUDA(cudaMemcpyAsync(&nu, pos.p + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CRG_CUDA(cudaStreamSynchronize(st));
+        if ((int64_t)nu != n) {
+            dedupe_kernel<<<ceil_div(n, 256), 256, 0, st>>>(ka, (const double *)va, flags.p, pos.p, n, kb, (double *)vb);
+            CRG_LAUNCH_CHECK();
+            std::swap(ka, kb); std::swap(va, vb);
+            nnz = nu;
+        }
+    }
+    if (nnz >= ((int64_t)1 << 31)) return set_error(CRG_ERR_NOMEM, "nnz=%lld exceeds int32 indexing", (long long)nnz);
+    R->nnz = nnz;
+    // CSR(A)
+    Csr &A = R->A;
+    A.n_rows = R->n_dst; A.n_cols = R->n_src; A.nnz = nnz;
+    CRG_TRY(A.rowptr.alloc((size_t)A.n_rows + 1, st));
+    CRG_TRY(A.colidx.alloc((size_t)nnz, st));
+    CRG_TRY(A.vals.alloc((size_t)nnz, st));
+    CRG_CUDA(cudaMemsetAsync(A.rowptr.p, 0, sizeof(int32_t) * (size_t)(A.n_rows + 1), st));
+    if (nnz > 0) {
+        split_csr_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(ka, (const double *)va, nnz, A.n_rows, A.rowptr.p,
+                                                               A.colidx.p, A.vals.p);
+        CRG_LAUNCH_CHECK();
+    }
+    *t_sort_csr1 = (int)tm.ev.size();
+    CRG_TRY(tm.mark());
+    // CSR(A^T): swap the key halves and (stably) sort by the new high word only
+    R->has_At = false;
+    if (R->opts.build_transpose) {
+        Csr &T = R->At;
+        T.n_rows = R->n_src; T.n_cols = R->n_dst; T.nnz = nnz;
+        CRG_TRY(T.rowptr.alloc((size_t)T.n_rows + 1, st));
+        CRG_TRY(T.colidx.alloc((size_t)nnz, st));
+        CRG_TRY(T.vals.alloc((size_t)nnz, st));
+        CRG_CUDA(cudaMemsetAsync(T.rowptr.p, 0, sizeof(int32_t) * (size_t)(T.n_rows + 1), st));
+        int p3 = 0;
+        if (nnz > 0) {
+            swap_key_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(ka, nnz, ka);
+            CRG_LAUNCH_CHECK();
+            CRG_TRY(radix_sort_pairs(ka, va, kb, vb, nnz, 32, 32 + bits_src, &inb, &p3, st));
+            if (inb) { std::swap(ka, kb); std::swap(va, vb); }
+            split_csr_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(ka, (const double *)va, nnz, T.n_rows, T.rowptr.p,
+                                                                   T.colidx.p, T.vals.p);
+            CRG_LAUNCH_CHECK();
+        }
+        R->stats.sort_passes_csc = p3;
+        R->has_At = true;
+    }
+    *t_sort_csc1 = (int)tm.ev.size();
+    CRG_TRY(tm.mark());
+    return CRG_OK;
+}
+
+static int do_normalize(crg_regridder *R) {
+    cudaStream_t st = R->stream;
+    if (R->nnz == 0) return CRG_OK;   // maximum() of an empty matrix: nothing to scale
+    CRG_TRY(R->scratch_max.alloc(1, st));
+    CRG_CUDA(cudaMemsetAsync(R->scratch_max.p, 0, sizeof(double), st));
+    max_kernel<<<296, 256, 0, st>>>(R->A.vals.p, R->nnz, R->scratch_max.p);
+    CRG_LAUNCH_CHECK();
+    div_by_kernel<<<296, 256, 0, st>>>(R->A.vals.p, R->nnz, R->scratch_max.p);
+    if (R->has_At) div_by_kernel<<<296, 256, 0, st>>>(R->At.vals.p, R->nnz, R->scratch_max.p);
+    div_by_kernel<<<148, 256, 0, st>>>(R->dst_areas.p, R->n_dst, R->scratch_max.p);
+    div_by_kernel<<<148, 256, 0, st>>>(R->src_areas.p, R->n_src, R->scratch_max.p);
+    CRG_LAUNCH_CHECK();
+    return CRG_OK;
+}
+
+template <int DIM>
+static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *src) {
+    cudaStream_t st = R->stream;
+    crg_build_stats &S = R->stats;
+    const double t_begin = now_ms();
+    Timer tm(st);
+
+    // ---- stage inputs -------------------------------------------------------------------
+    DevCells gd, gs;
+    CRG_TRY(stage_cells(dst, DIM, st, &gd, "dst"));
+    CRG_TRY(stage_cells(src, DIM, st, &gs, "src"));
+    CRG_CUDA(cudaStreamSynchronize(st));
+    S.ms_h2d = now_ms() - t_begin;
+    const int64_t nd = R->n_dst, ns = R->n_src;
+    const double r2 = DIM == 3 ? R->opts.radius * R->opts.radius : 1.0;
+
+    CRG_TRY(tm.mark());   // 0
+    // ---- K4: areas + orientation ----------------------------------------------------------
+    CRG_TRY(R->dst_areas.alloc((size_t)nd, st));
+    CRG_TRY(R->src_areas.alloc((size_t)ns, st));
+    CRG_TRY(gd.flip.alloc((size_t)nd, st));
+    CRG_TRY(gs.flip.alloc((size_t)ns, st));
+    DevBuf<unsigned int> nflip;
+    CRG_TRY(nflip.alloc(2, st));
+    CRG_CUDA(cudaMemsetAsync(nflip.p, 0, 2 * sizeof(unsigned int), st));
+    if (nd) cell_area_kernel<DIM><<<ceil_div(nd, 256), 256, 0, st>>>(gd.view, r2, R->dst_areas.p, gd.flip.p, nflip.p);
+    if (ns) cell_area_kernel<DIM><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, r2, R->src_areas.p, gs.flip.p, nflip.p + 1);
+    CRG_LAUNCH_CHECK();
+    gd.view.flip = gd.flip.p;
+    gs.view.flip = gs.flip.p;
+    CRG_TRY(tm.mark());   // 1
+
+    // ---- K1: bounds -------------------------------------------------------------------------
+    CRG_TRY(gd.diam.alloc((size_t)nd, st));
+    CRG_TRY(gs.diam.alloc((size_t)ns, st));
+    DevBuf<BPStats> dstats;
+    CRG_TRY(dstats.alloc(2, st));
+    BPStats hst[2];
+    memset(hst, 0, sizeof(hst));
+    for (int k = 0; k < 2; ++k) { hst[k].lo[0] = hst[k].lo[1] = ~0ull; hst[k].hi[0] = hst[k].hi[1] = 0ull; }
+    CRG_CUDA(cudaMemcpyAsync(dstats.p, hst, sizeof(hst), cudaMemcpyHostToDevice, st));
+    const double big_chord = 2.0 * std::sin(BP_BIG_ANGLE / 2.0);
+    if (nd) bp_bounds_kernel<DIM><<<ceil_div(nd, 256), 256, 0, st>>>(gd.view, gd.diam.p, dstats.p, (float)big_chord);
+    if (ns) bp_bounds_kernel<DIM><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, gs.diam.p, dstats.p + 1, (float)big_chord);
+    CRG_LAUNCH_CHECK();
+    CRG_CUDA(cudaMemcpyAsync(hst, dstats.p, sizeof(hst), cudaMemcpyDeviceToHost, st));
+    CRG_CUDA(cudaStreamSynchronize(st));
+    CRG_TRY(tm.mark());   // 2
+
+    // ---- choose the bin grid ----------------------------------------------------------------
+    BPParams P;
+    memset(&P, 0, sizeof(P));
+    P.dim = DIM;
+    P.big_chord = big_chord;
+    const int NB_CAP = 2048;
+    const double mean_src = hst[1].count ? hst[1].sum_diam / (double)hst[1].count : 0.0;
+    if (DIM == 3) {
+        P.nfaces = 6;
+        double margin = hst[0].count ? 1.4 * 2.0 * std::asin(std::fmin(1.0, 0.5 * (double)hst[0].max_diam)) + 1e-6 : 0.0;
+        if (margin > 0.3) margin = 0.3;
+        const double A = 0.25 * M_PI + margin;
+        double h = 0.75 * mean_src;
+        if (!(h > 2.0 * A / NB_CAP)) h = 2.0 * A / NB_CAP;
+        if (hst[1].count == 0) h = 2.0 * A;
+        int nb = (int)std::ceil(2.0 * A / h);
+        if (nb < 1) nb = 1;
+        if (nb > NB_CAP) nb = NB_CAP;
+        h = 2.0 * A / nb;
+        P.nbx = P.nby = nb;
+        P.ox = P.oy = -A;
+        P.hx = P.hy = A;
+        P.inv_hq = BP_SUB / h;
+        P.eps = 1e-9;
+        S.bin_size = h;
+    } else {
+        P.nfaces = 1;
+        double lo[2], hi[2];
+        for (int k = 0; k < 2; ++k) {
+            const unsigned long long l = hst[0].lo[k] < hst[1].lo[k] ? hst[0].lo[k] : hst[1].lo[k];
+            const unsigned long long u = hst[0].hi[k] > hst[1].hi[k] ? hst[0].hi[k] : hst[1].hi[k];
+            lo[k] = (nd + ns) ? ordered_bits_to_double(l) : 0.0;
+            hi[k] = (nd + ns) ? ordered_bits_to_double(u) : 1.0;
+        }
+        const double ext = std::fmax(std::fmax(hi[0] - lo[0], hi[1] - lo[1]),
+                                     std::fmax(std::fmax(std::fabs(lo[0]), std::fabs(hi[0])),
+                                               std::fmax(std::fabs(lo[1]), std::fabs(hi[1]))));
+        P.eps = 1e-9 * (ext > 0 ? ext : 1.0);
+        P.ox = lo[0] - 4 * P.eps; P.oy = lo[1] - 4 * P.eps;
+        P.hx = hi[0] + 4 * P.eps; P.hy = hi[1] + 4 * P.eps;
+        const double Lx = P.hx - P.ox, Ly = P.hy - P.oy;
+        double h = 0.75 * mean_src;
+        const double hmin = std::fmax(Lx, Ly) / NB_CAP;
+        if (!(h > hmin)) h = hmin;
+        if (!(h > 0)) h = 1.0;
+        P.nbx = (int)std::fmin((double)NB_CAP, std::fmax(1.0, std::ceil(Lx / h)));
+        P.nby = (int)std::fmin((double)NB_CAP, std::fmax(1.0, std::ceil(Ly / h)));
+        P.inv_hq = BP_SUB / h;
+        P.big_chord = 1e300;
+        S.bin_size = h;
+    }
+    const size_t nbins = (size_t)P.nfaces * P.nbx * P.nby;
+    S.n_bins = (int64_t)nbins;
+
+    // ---- K2a: bin the source cells (count / scan / fill) ------------------------------------
+    DevBuf<uint32_t> bin_count, bin_start, counters;
+    DevBuf<int32_t> big_src, big_dst;
+    CRG_TRY(bin_count.alloc(nbins + 1, st));
+    CRG_TRY(bin_start.alloc(nbins + 1, st));
+    CRG_TRY(counters.alloc(4, st));
+    CRG_TRY(big_src.alloc((size_t)ns, st));
+    CRG_TRY(big_dst.alloc((size_t)nd, st));
+    CRG_CUDA(cudaMemsetAsync(bin_count.p, 0, sizeof(uint32_t) * (nbins + 1), st));
+    CRG_CUDA(cudaMemsetAsync(counters.p, 0, sizeof(uint32_t) * 4, st));
+    if (ns) bp_bin_kernel<DIM, false><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, gs.diam.p, P, bin_count.p, nullptr,
+                                                                          nullptr, big_src.p, counters.p);
+    CRG_LAUNCH_CHECK();
+    CRG_TRY((exclusive_scan<uint32_t, uint32_t>(bin_count.p, (int64_t)nbins, bin_start.p, st)));
+    uint32_t h_entries = 0, h_counters[4] = {0, 0, 0, 0};
+    CRG_CUDA(cudaMemcpyAsync(&h_entries, bin_start.p + nbins, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CRG_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, st));
+    CRG_CUDA(cudaStreamSynchronize(st));
+    const int n_big_src = (int)h_counters[0];
+    S.n_bin_entries = h_entries;
+    S.n_big_src = n_big_src;
+    DevBuf<int4> entries;
+    CRG_TRY(entries.alloc((size_t)h_entries, st));
+    CRG_CUDA(cudaMemsetAsync(bin_count.p, 0, sizeof(uint32_t) * (nbins + 1), st));
+    if (ns) bp_bin_kernel<DIM, true><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, gs.diam.p, P, bin_count.p, bin_start.p,
+                                                                         entries.p, nullptr, nullptr);
+    CRG_LAUNCH_CHECK();
+    CRG_TRY(tm.mark());   // 3
+
+    // ---- K2b: destination queries (count / scan / fill) ---------------------------------------
+    DevBuf<uint32_t> cand_count;
+    DevBuf<int64_t> cand_off;
+    CRG_TRY(cand_count.alloc((size_t)nd + 1, st));
+    CRG_TRY(cand_off.alloc((size_t)nd + 1, st));
+    if (nd) bp_query_kernel<DIM, false><<<ceil_div(nd, 128), 128, 0, st>>>(
+        gd.view, gd.diam.p, P, bin_start.p, entries.p, big_src.p, n_big_src, ns, cand_count.p, nullptr, nullptr,
+        big_dst.p, counters.p + 1);
+    CRG_LAUNCH_CHECK();
+    CRG_TRY((exclusive_scan<uint32_t, int64_t>(cand_count.p, nd, cand_off.p, st)));
+    int64_t n_cand = 0;
+    CRG_CUDA(cudaMemcpyAsync(&n_cand, cand_off.p + nd, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CRG_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, st));
+    CRG_CUDA(cudaStreamSynchronize(st));
+    const int n_big_dst = (int)h_counters[1];
+    S.n_candidates = n_cand;
+    S.n_big_dst = n_big_dst;
+    if (n_cand >= ((int64_t)1 << 32))
+        return set_error(CRG_ERR_NOMEM, "candidate pair count %lld exceeds 2^32", (long long)n_cand);
+    DevBuf<int2> pairs;
+    CRG_TRY(pairs.alloc((size_t)n_cand, st));
+    if (nd) bp_query_kernel<DIM, true><<<ceil_div(nd, 128), 128, 0, st>>>(
+        gd.view, gd.diam.p, P, bin_start.p, entries.p, big_src.p, n_big_src, ns, nullptr, cand_off.p, pairs.p, nullptr,
+        nullptr);
+    CRG_LAUNCH_CHECK();
+    if (n_big_dst && ns) {
+        dim3 grid((unsigned)std::min<int64_t>(ceil_div(ns, 256), 1024), (unsigned)n_big_dst);
+        bp_fill_big_dst_kernel<<<grid, 256, 0, st>>>(big_dst.p, cand_off.p, ns, pairs.p);
+        CRG_LAUNCH_CHECK();
+    }
+    entries.release(); bin_count.release(); bin_start.release();
+    CRG_TRY(tm.mark());   // 4
+
+    // ---- K3: clip + area, compaction ------------------------------------------------------------
+    DevBuf<uint64_t> coo_key;
+    DevBuf<double> coo_val;
+    DevBuf<unsigned long long> nkeep;
+    CRG_TRY(coo_key.alloc((size_t)n_cand, st));
+    CRG_TRY(coo_val.alloc((size_t)n_cand, st));
+    CRG_TRY(nkeep.alloc(1, st));
+    CRG_CUDA(cudaMemsetAsync(nkeep.p, 0, sizeof(unsigned long long), st));
+    if (n_cand > 0) {
+        const bool fixed4 = !dst->offsets && !src->offsets && dst->nv <= 4 && src->nv <= 4;
+        if (fixed4) {
+            constexpr int NT = 128, MW = 8;
+            const size_t smem = sizeof(double) * 2 * MW * DIM * NT;
+            auto kern = clip_kernel<DIM, NT, MW>;
+            CRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<ceil_div(n_cand, NT), NT, smem, st>>>(gd.view, gs.view, pairs.p, n_cand, r2, R->opts.area_threshold,
+                                                         coo_key.p, coo_val.p, nkeep.p);
+        } else {
+            constexpr int NT = 64, MW = 2 * CRG_MAX_VERTS;
+            const size_t smem = sizeof(double) * 2 * MW * DIM * NT;
+            auto kern = clip_kernel<DIM, NT, MW>;
+            CRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<ceil_div(n_cand, NT), NT, smem, st>>>(gd.view, gs.view, pairs.p, n_cand, r2, R->opts.area_threshold,
+                                                         coo_key.p, coo_val.p, nkeep.p);
+        }
+        CRG_LAUNCH_CHECK();
+    }
+    unsigned long long h_keep = 0;
+    CRG_CUDA(cudaMemcpyAsync(&h_keep, nkeep.p, sizeof(h_keep), cudaMemcpyDeviceToHost, st));
+    CRG_CUDA(cudaStreamSynchronize(st));
+    if (R->opts.keep_candidates) {
+        R->cand_pairs = std::move(pairs);
+        R->n_cand_kept = n_cand;
+    } else {
+        pairs.release();
+    }
+    CRG_TRY(tm.mark());   // 5
+
+    // ---- K5: assembly ------------------------------------------------------------------------------
+    int t0 = 0, t1 = 0, t2 = 0;
+    CRG_TRY(assemble(R, coo_key, coo_val, (int64_t)h_keep, true, tm, &t0, &t1, &t2));
+    coo_key.release(); coo_val.release();
+
+    // ---- K6: normalize ------------------------------------------------------------------------------
+    if (R->opts.normalize) CRG_TRY(do_normalize(R));
+    CRG_TRY(tm.mark());   // last
+    CRG_CUDA(cudaStreamSynchronize(st));
+    const int last = (int)tm.ev.size() - 1;
+    S.n_dst = nd; S.n_src = ns; S.nnz = R->nnz;
+    S.ms_areas = tm.ms(0, 1);
+    S.ms_bounds = tm.ms(1, 2);
+    S.ms_bin = tm.ms(2, 3);
+    S.ms_query = tm.ms(3, 4);
+    S.ms_clip = tm.ms(4, 5);
+    S.ms_sort_csr = tm.ms(t0, t1);
+    S.ms_sort_csc = tm.ms(t1, t2);
+    S.ms_finish = tm.ms(t2, last);
+    S.ms_device = tm.ms(0, last);
+    S.ms_total = now_ms() - t_begin;
+    return CRG_OK;
+}
+
+static int new_handle(const crg_options *opts, crg_regridder **out, DeviceGuard &guard) {
+    CRG_TRY(check_device_available());
+    int ndev = 0;
+    CRG_CUDA(cudaGetDeviceCount(&ndev));
+    if (opts->device >= ndev) return set_error(CRG_ERR_INVALID, "device %d out of range (%d devices)", opts->device, ndev);
+    CRG_TRY(guard.set(opts->device));
+    crg_regridder *R = new (std::nothrow) crg_regridder();
+    if (!R) return set_error(CRG_ERR_NOMEM, "out of host memory");
+    R->opts = *opts;
+    memset(&R->stats, 0, sizeof(R->stats));
+    cudaError_t e = cudaGetDevice(&R->device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&R->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete R; return fail_cuda(e, "cudaStreamCreate", __FILE__, __LINE__); }
+    R->stream = R->own_stream;
+    // keep freed blocks in the pool: repeated builds/applies do not hit the driver allocator
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, R->device) == cudaSuccess) {
+        uint64_t thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
+    *out = R;
+    return CRG_OK;
+}
+
+static void destroy_handle(crg_regridder *R) {
+    if (!R) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(R->device);
+    cudaStream_t st = R->own_stream;
+    // release everything on the handle's own stream, then drain it
+    auto rebind = [&](auto &buf) { buf.s = st; buf.release(); };
+    rebind(R->A.rowptr); rebind(R->A.colidx); rebind(R->A.vals);
+    rebind(R->At.rowptr); rebind(R->At.colidx); rebind(R->At.vals);
+    rebind(R->dst_areas); rebind(R->src_areas); rebind(R->scratch_max); rebind(R->cand_pairs);
+    rebind(R->stage_src); rebind(R->stage_dst);
+    if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    delete R;
+    if (prev >= 0) cudaSetDevice(prev);
+    cudaGetLastError();
+}
+
+static int apply_impl(crg_regridder *R, int transpose, int divide, double *dst, const double *src, int64_t K,
+                      int64_t ld_dst, int64_t ld_src, int level_fastest, bool allow_host, bool sync) {
+    if (!R || !dst || !src) return set_error(CRG_ERR_INVALID, "crg_apply: null argument");
+    if (K < 1) return set_error(CRG_ERR_INVALID, "crg_apply: K=%lld must be >= 1", (long long)K);
+    if (transpose && !R->has_At) return set_error(CRG_ERR_INVALID, "crg_apply: transpose requested but the regridder was built with build_transpose=0");
+    const Csr &M = transpose ? R->At : R->A;
+    const double *areas = transpose ? R->src_areas.p : R->dst_areas.p;
+    const int64_t n_out = M.n_rows, n_in = M.n_cols;
+    if (K == 1) { if (ld_dst <= 0) ld_dst = level_fastest ? 1 : n_out; if (ld_src <= 0) ld_src = level_fastest ? 1 : n_in; }
+    if (level_fastest) {
+        if (ld_dst < K || ld_src < K) return set_error(CRG_ERR_INVALID, "crg_apply: level-fastest leading dimensions (%lld, %lld) smaller than K=%lld", (long long)ld_dst, (long long)ld_src, (long long)K);
+    } else {
+        if (ld_dst < n_out || ld_src < n_in) return set_error(CRG_ERR_INVALID, "crg_apply: cell-fastest leading dimensions (%lld, %lld) smaller than (%lld, %lld)", (long long)ld_dst, (long long)ld_src, (long long)n_out, (long long)n_in);
+    }
+    DeviceGuard guard;
+    CRG_TRY(guard.set(R->device));
+    cudaStream_t st = R->stream;
+    const bool src_dev = is_device_ptr(src), dst_dev = is_device_ptr(dst);
+    if ((!src_dev || !dst_dev) && !allow_host)
+        return set_error(CRG_ERR_INVALID, "crg_apply_async: host pointers are not allowed");
+    const size_t src_elems = level_fastest ? (size_t)(n_in - 1) * ld_src + K : (size_t)(K - 1) * ld_src + n_in;
+    const size_t dst_elems = level_fastest ? (size_t)(n_out - 1) * ld_dst + K : (size_t)(K - 1) * ld_dst + n_out;
+    const double *xs = src;
+    double *yd = dst;
+    if (!src_dev) {
+        if (R->stage_src.n < src_elems) CRG_TRY(R->stage_src.alloc(src_elems, st));
+        CRG_CUDA(cudaMemcpyAsync(R->stage_src.p, src, sizeof(double) * src_elems, cudaMemcpyHostToDevice, st));
+        xs = R->stage_src.p;
+    }
+    if (!dst_dev) {
+        if (R->stage_dst.n < dst_elems) CRG_TRY(R->stage_dst.alloc(dst_elems, st));
+        yd = R->stage_dst.p;
+        if ((level_fastest ? ld_dst != K : ld_dst != n_out))   // padded layout: keep the caller's padding bytes
+            CRG_CUDA(cudaMemcpyAsync(yd, dst, sizeof(double) * dst_elems, cudaMemcpyHostToDevice, st));
+    }
+    if (n_out > 0) {
+        if (K == 1 && (level_fastest ? (ld_src == 1 && ld_dst == 1) : true)) {
+            const int nblk = ceil_div(n_out, 32 * (SPMV_THREADS / 32));
+            if (divide) spmv_kernel<true><<<nblk, SPMV_THREADS, 0, st>>>(M.rowptr.p, M.colidx.p, M.vals.p, xs, yd, areas, n_out);
+            else spmv_kernel<false><<<nblk, SPMV_THREADS, 0, st>>>(M.rowptr.p, M.colidx.p, M.vals.p, xs, yd, areas, n_out);
+        } else if (level_fastest) {
+            const int nblk = ceil_div(n_out, 8);
+#define CRG_LF(KT)                                                                                                   \
+    do {                                                                                                             \
+        if (divide) spmm_lf_kernel<KT, true><<<nblk, 256, 0, st>>>(M.rowptr.p, M.colidx.p, M.vals.p, xs, yd, areas, n_out, K, ld_src, ld_dst); \
+        else spmm_lf_kernel<KT, false><<<nblk, 256, 0, st>>>(M.rowptr.p, M.colidx.p, M.vals.p, xs, yd, areas, n_out, K, ld_src, ld_dst);      \
+    } while (0)
+            if (K <= 32) CRG_LF(1);
+            else if (K <= 64) CRG_LF(2);
+            else CRG_LF(4);
+#undef CRG_LF
+        } else {
+            constexpr int KC = 8;
+            dim3 grid((unsigned)ceil_div(n_out, 128), (unsigned)ceil_div(K, KC));
+            if (divide) spmm_cf_kernel<KC, true><<<grid, 128, 0, st>>>(M.rowptr.p, M.colidx.p, M.vals.p, xs, yd, areas, n_out, K, ld_src, ld_dst);
+            else spmm_cf_kernel<KC, false><<<grid, 128, 0, st>>>(M.rowptr.p, M.colidx.p, M.vals.p, xs, yd, areas, n_out, K, ld_src, ld_dst);
+        }
+        CRG_LAUNCH_CHECK();
+    }
+    if (!dst_dev) CRG_CUDA(cudaMemcpyAsync(dst, yd, sizeof(double) * dst_elems, cudaMemcpyDeviceToHost, st));
+    if (sync || !dst_dev || !src_dev) CRG_CUDA(cudaStreamSynchronize(st));
+    return CRG_OK;
+}
+
+template <typename T>
+static int copy_out(T *dst, const T *dev_src, size_t n, cudaStream_t st) {
+    if (!dst || n == 0) return CRG_OK;
+    CRG_CUDA(cudaMemcpyAsync(dst, dev_src, sizeof(T) * n, is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    return CRG_OK;
+}
+
+static int export_csr_matrix(const crg_regridder *R, const Csr &M, int32_t base, int64_t *ptr, int64_t *idx, double *val) {
+    DeviceGuard guard;
+    CRG_TRY(guard.set(R->device));
+    cudaStream_t st = R->stream;
+    std::vector<int32_t> tmp;
+    if (ptr) {
+        tmp.resize((size_t)M.n_rows + 1);
+        CRG_CUDA(cudaMemcpyAsync(tmp.data(), M.rowptr.p, sizeof(int32_t) * tmp.size(), cudaMemcpyDeviceToHost, st));
+        CRG_CUDA(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < tmp.size(); ++i) ptr[i] = (int64_t)tmp[i] + base;
+    }
+    if (idx && M.nnz) {
+        tmp.resize((size_t)M.nnz);
+        CRG_CUDA(cudaMemcpyAsync(tmp.data(), M.colidx.p, sizeof(int32_t) * tmp.size(), cudaMemcpyDeviceToHost, st));
+        CRG_CUDA(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < (size_t)M.nnz; ++i) idx[i] = (int64_t)tmp[i] + base;
+    }
+    if (val && M.nnz) {
+        CRG_CUDA(cudaMemcpyAsync(val, M.vals.p, sizeof(double) * (size_t)M.nnz, cudaMemcpyDeviceToHost, st));
+        CRG_CUDA(cudaStreamSynchronize(st));
+    }
+    return CRG_OK;
+}
+
+}  // namespace crg
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char *crg_last_error(void) { return g_err; }
+const char *crg_version(void) { return "crg_b200 0.1.0 (sm_100a)"; }
+
+int crg_device_count(int32_t *count) {
+    if (!count) return set_error(CRG_ERR_INVALID, "null count");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+    *count = n;
+    return CRG_OK;
+}
+
+int crg_options_init(crg_options *o) {
+    if (!o) return set_error(CRG_ERR_INVALID, "null options");
+    memset(o, 0, sizeof(*o));
+    o->manifold = CRG_SPHERICAL;
+    o->normalize = 0;
+    o->radius = 1.0;
+    o->area_threshold = 0.0;
+    o->device = -1;
+    o->build_transpose = 1;
+    o->keep_candidates = 0;
+    return CRG_OK;
+}
+
+int crg_build(const crg_options *opts, const crg_cells *dst, const crg_cells *src, crg_regridder **out) {
+    if (!opts || !out) return set_error(CRG_ERR_INVALID, "crg_build: null argument");
+    *out = nullptr;
+    if (opts->manifold != CRG_PLANAR && opts->manifold != CRG_SPHERICAL)
+        return set_error(CRG_ERR_INVALID, "crg_build: unknown manifold %d", opts->manifold);
+    if (!(opts->radius > 0.0)) return set_error(CRG_ERR_INVALID, "crg_build: radius must be positive");
+    CRG_TRY(validate_cells(dst, "dst"));
+    CRG_TRY(validate_cells(src, "src"));
+    DeviceGuard guard;
+    crg_regridder *R = nullptr;
+    CRG_TRY(new_handle(opts, &R, guard));
+    R->n_dst = dst->ncells;
+    R->n_src = src->ncells;
+    int rc = opts->manifold == CRG_SPHERICAL ? build_impl<3>(R, dst, src) : build_impl<2>(R, dst, src);
+    if (rc != CRG_OK) { cudaStreamSynchronize(R->stream); destroy_handle(R); return rc; }
+    *out = R;
+    return CRG_OK;
+}
+
+int crg_build_from_coo(const crg_options *opts, int64_t n_dst, int64_t n_src, int64_t nnz, const int64_t *dst_idx,
+                       const int64_t *src_idx, const double *area, const double *dst_areas, const double *src_areas,
+                       crg_regridder **out) {
+    if (!opts || !out) return set_error(CRG_ERR_INVALID, "crg_build_from_coo: null argument");
+    *out = nullptr;
+    if (n_dst < 0 || n_src < 0 || nnz < 0 || n_dst >= ((int64_t)1 << 31) || n_src >= ((int64_t)1 << 31))
+        return set_error(CRG_ERR_INVALID, "crg_build_from_coo: bad sizes");
+    if (nnz > 0 && (!dst_idx || !src_idx || !area)) return set_error(CRG_ERR_INVALID, "crg_build_from_coo: null triples");
+    if (!is_device_ptr(dst_idx))
+        for (int64_t k = 0; k < nnz; ++k)
+            if (dst_idx[k] < 0 || dst_idx[k] >= n_dst || src_idx[k] < 0 || src_idx[k] >= n_src)
+                return set_error(CRG_ERR_INVALID, "crg_build_from_coo: index out of range at entry %lld", (long long)k);
+    DeviceGuard guard;
+    crg_regridder *R = nullptr;
+    CRG_TRY(new_handle(opts, &R, guard));
+    R->n_dst = n_dst;
+    R->n_src = n_src;
+    auto body = [&]() -> int {
+        cudaStream_t st = R->stream;
+        const double t0 = now_ms();
+        Timer tm(st);
+        DevBuf<int64_t> dr, dc;
+        DevBuf<uint64_t> keys;
+        DevBuf<double> vals;
+        const size_t n1 = (size_t)(nnz > 0 ? nnz : 1);
+        CRG_TRY(dr.alloc(n1, st)); CRG_TRY(dc.alloc(n1, st)); CRG_TRY(keys.alloc(n1, st)); CRG_TRY(vals.alloc(n1, st));
+        if (nnz) {
+            CRG_CUDA(cudaMemcpyAsync(dr.p, dst_idx, sizeof(int64_t) * nnz, cudaMemcpyDefault, st));
+            CRG_CUDA(cudaMemcpyAsync(dc.p, src_idx, sizeof(int64_t) * nnz, cudaMemcpyDefault, st));
+            CRG_CUDA(cudaMemcpyAsync(vals.p, area, sizeof(double) * nnz, cudaMemcpyDefault, st));
+            pack_coo_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(dr.p, dc.p, nnz, keys.p);
+            CRG_LAUNCH_CHECK();
+        }
+        CRG_TRY(R->dst_areas.alloc((size_t)n_dst, st));
+        CRG_TRY(R->src_areas.alloc((size_t)n_src, st));
+        if (dst_areas && n_dst) CRG_CUDA(cudaMemcpyAsync(R->dst_areas.p, dst_areas, sizeof(double) * n_dst, cudaMemcpyDefault, st));
+        else CRG_CUDA(cudaMemsetAsync(R->dst_areas.p, 0, sizeof(double) * (size_t)(n_dst > 0 ? n_dst : 1), st));
+        if (src_areas && n_src) CRG_CUDA(cudaMemcpyAsync(R->src_areas.p, src_areas, sizeof(double) * n_src, cudaMemcpyDefault, st));
+        else CRG_CUDA(cudaMemsetAsync(R->src_areas.p, 0, sizeof(double) * (size_t)(n_src > 0 ? n_src : 1), st));
+        CRG_TRY(tm.mark());
+        int a = 0, b = 0, c = 0;
+        CRG_TRY(assemble(R, keys, vals, nnz, false, tm, &a, &b, &c));
+        if (R->opts.normalize) CRG_TRY(do_normalize(R));
+        CRG_TRY(tm.mark());
+        CRG_CUDA(cudaStreamSynchronize(st));
+        crg_build_stats &S = R->stats;
+        S.n_dst = n_dst; S.n_src = n_src; S.nnz = R->nnz; S.n_candidates = nnz;
+        S.ms_sort_csr = tm.ms(a, b); S.ms_sort_csc = tm.ms(b, c);
+        S.ms_device = tm.ms(0, (int)tm.ev.size() - 1);
+        S.ms_total = now_ms() - t0;
+        return CRG_OK;
+    };
+    int rc = body();
+    if (rc != CRG_OK) { cudaStreamSynchronize(R->stream); destroy_handle(R); return rc; }
+    *out = R;
+    return CRG_OK;
+}
+
+int crg_free(crg_regridder *r) {
+    destroy_handle(r);
+    return CRG_OK;
+}
+
+int crg_dims(const crg_regridder *r, int64_t *n_dst, int64_t *n_src, int64_t *nnz) {
+    if (!r) return set_error(CRG_ERR_INVALID, "null regridder");
+    if (n_dst) *n_dst = r->n_dst;
+    if (n_src) *n_src = r->n_src;
+    if (nnz) *nnz = r->nnz;
+    return CRG_OK;
+}
+
+int crg_stats(const crg_regridder *r, crg_build_stats *s) {
+    if (!r || !s) return set_error(CRG_ERR_INVALID, "null argument");
+    *s = r->stats;
+    return CRG_OK;
+}
+
+int crg_areas(const crg_regridder *r, double *dst_areas, double *src_areas) {
+    if (!r) return set_error(CRG_ERR_INVALID, "null regridder");
+    DeviceGuard guard;
+    CRG_TRY(guard.set(r->device));
+    CRG_TRY(copy_out(dst_areas, r->dst_areas.p, (size_t)r->n_dst, r->stream));
+    CRG_TRY(copy_out(src_areas, r->src_areas.p, (size_t)r->n_src, r->stream));
+    CRG_CUDA(cudaStreamSynchronize(r->stream));
+    return CRG_OK;
+}
+
+int crg_export_csc(const crg_regridder *r, int32_t base, int64_t *colptr, int64_t *rowval, double *nzval) {
+    if (!r) return set_error(CRG_ERR_INVALID, "null regridder");
+    if (!r->has_At) return set_error(CRG_ERR_INVALID, "crg_export_csc needs build_transpose=1");
+    return export_csr_matrix(r, r->At, base, colptr, rowval, nzval);
+}
+
+int crg_export_csr(const crg_regridder *r, int32_t base, int64_t *rowptr, int64_t *colval, double *nzval) {
+    if (!r) return set_error(CRG_ERR_INVALID, "null regridder");
+    return export_csr_matrix(r, r->A, base, rowptr, colval, nzval);
+}
+
+int crg_candidates(const crg_regridder *r, int64_t *src_idx, int64_t *dst_idx) {
+    if (!r) return set_error(CRG_ERR_INVALID, "null regridder");
+    if (!r->opts.keep_candidates) return set_error(CRG_ERR_INVALID, "regridder was built without keep_candidates");
+    DeviceGuard guard;
+    CRG_TRY(guard.set(r->device));
+    std::vector<int2> tmp((size_t)r->n_cand_kept);
+    if (r->n_cand_kept) {
+        CRG_CUDA(cudaMemcpyAsync(tmp.data(), r->cand_pairs.p, sizeof(int2) * tmp.size(), cudaMemcpyDeviceToHost, r->stream));
+        CRG_CUDA(cudaStreamSynchronize(r->stream));
+    }
+    for (size_t i = 0; i < tmp.size(); ++i) {
+        if (src_idx) src_idx[i] = tmp[i].x;
+        if (dst_idx) dst_idx[i] = tmp[i].y;
+    }
+    return CRG_OK;
+}
+
+int crg_normalize(crg_regridder *r) {
+    if (!r) return set_error(CRG_ERR_INVALID, "null regridder");
+    DeviceGuard guard;
+    CRG_TRY(guard.set(r->device));
+    CRG_TRY(do_normalize(r));
+    CRG_CUDA(cudaStreamSynchronize(r->stream));
+    return CRG_OK;
+}
+
+int crg_apply(crg_regridder *r, int32_t transpose, int32_t divide, double *dst, const double *src, int64_t K,
+              int64_t ld_dst, int64_t ld_src, int32_t level_fastest) {
+    return apply_impl(r, transpose, divide, dst, src, K, ld_dst, ld_src, level_fastest, true, true);
+}
+
+int crg_apply_async(crg_regridder *r, int32_t transpose, int32_t divide, double *dst, const double *src, int64_t K,
+                    int64_t ld_dst, int64_t ld_src, int32_t level_fastest) {
+    return apply_impl(r, transpose, divide, dst, src, K, ld_dst, ld_src, level_fastest, false, false);
+}
+
+int crg_set_stream(crg_regridder *r, void *s) {
+    if (!r) return set_error(CRG_ERR_INVALID, "null regridder");
+    DeviceGuard guard;
+    CRG_TRY(guard.set(r->device));
+    CRG_CUDA(cudaStreamSynchronize(r->stream));
+    r->stream = s ? (cudaStream_t)s : r->own_stream;
+    return CRG_OK;
+}
+
+int crg_synchronize(crg_regridder *r) {
+    if (!r) return set_error(CRG_ERR_INVALID, "null regridder");
+    DeviceGuard guard;
+    CRG_TRY(guard.set(r->device));
+    CRG_CUDA(cudaStreamSynchronize(r->stream));
+    return CRG_OK;
+}
+
+int crg_apply_bytes(const crg_regridder *r, int32_t transpose, int32_t divide, int64_t K, int64_t *bytes) {
+    if (!r || !bytes) return set_error(CRG_ERR_INVALID, "null argument");
+    const int64_t n_out = transpose ? r->n_src : r->n_dst, n_in = transpose ? r->n_dst : r->n_src;
+    *bytes = 12 * r->nnz + 4 * (n_out + 1) + (divide ? 8 * n_out : 0) + 8 * K * (n_in + n_out);
+    return CRG_OK;
+}
+
+int crg_fp64_peak(int32_t device, double *tflops) {
+    if (!tflops) return set_error(CRG_ERR_INVALID, "null argument");
+    CRG_TRY(check_device_available());
+    DeviceGuard guard;
+    CRG_TRY(guard.set(device));
+    cudaDeviceProp prop;
+    int dev = 0;
+    CRG_CUDA(cudaGetDevice(&dev));
+    CRG_CUDA(cudaGetDeviceProperties(&prop, dev));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+    double *out = nullptr;
+    CRG_CUDA(cudaMalloc((void **)&out, sizeof(double) * (size_t)blocks * threads));
+    cudaEvent_t a, b;
+    CRG_CUDA(cudaEventCreate(&a));
+    CRG_CUDA(cudaEventCreate(&b));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CRG_CUDA(cudaEventRecord(a));
+        fp64_peak_kernel<<<blocks, threads>>>(out, iters);
+        CRG_CUDA(cudaEventRecord(b));
+        CRG_CUDA(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CRG_CUDA(cudaEventElapsedTime(&ms, a, b));
+        const double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
+    *tflops = best;
+    return CRG_OK;
+}
+
+}  // extern "C"

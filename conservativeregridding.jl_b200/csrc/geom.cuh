@@ -1,0 +1,212 @@
+// geom.cuh -- FP64 polygon geometry on the unit sphere / plane (device).
+//
+// Replaces, per candidate pair, DefaultIntersectionOperator
+// (/root/reference/src/regridder/regridder.jl:87-103): GO.intersection with
+// ConvexConvexSutherlandHodgman (great-circle half-space cuts) followed by GO.area, and per
+// cell GO.area (regridder.jl:165-178).  The arithmetic itself lives in GeometryOps.jl (not
+// in the reference tree); this is the published algorithm, written for one thread per pair
+// with the working polygon ping-ponged through shared memory.
+#pragma once
+#include "common.cuh"
+
+namespace crg {
+
+struct CellsView {
+    const double *verts;     // [ncells][nv][DIM] or ragged
+    const int32_t *off;      // nullptr => fixed nv
+    const uint8_t *flip;     // nullptr => every ring already CCW; else 1 = stored clockwise
+    int64_t ncells;
+    int nv;
+};
+
+struct d3 { double x, y, z; };
+
+__device__ __forceinline__ d3 operator-(d3 a, d3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ double dot(d3 a, d3 b) { return fma(a.x, b.x, fma(a.y, b.y, a.z * b.z)); }
+__device__ __forceinline__ d3 cross(d3 a, d3 b) {
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+
+// Accumulates spherical-excess half-angles as a complex product: the triangle (a, b, c)
+// contributes the angle of z = (1 + a.b + b.c + c.a) + i a.((b-a) x (c-a)), i.e. E/2, and
+// sum of angles = angle of the product -- one atan2 per polygon instead of one per
+// triangle.  The product is flushed through atan2 whenever its angle could leave
+// (-pi/2, pi/2), so arbitrarily large polygons stay exact.
+struct ExcessAcc {
+    double re = 1.0, im = 0.0, total = 0.0;
+    __device__ __forceinline__ void flush() {
+        total += atan2(im, re);
+        re = 1.0; im = 0.0;
+    }
+    __device__ __forceinline__ void add_triangle(d3 a, d3 b, d3 c) {
+        const double det = dot(a, cross(b - a, c - a));
+        const double den = 1.0 + dot(a, b) + dot(b, c) + dot(c, a);
+        if (!(den > 0.0)) {          // huge triangle: angle outside (-pi/2, pi/2)
+            flush();
+            total += atan2(det, den);
+            return;
+        }
+        const double nre = re * den - im * det;
+        const double nim = re * det + im * den;
+        re = nre; im = nim;
+        if (!(re > 0.0) || re > 1e200) flush();
+    }
+    __device__ __forceinline__ double area() {   // signed: CCW seen from outside positive
+        flush();
+        return 2.0 * total;
+    }
+};
+
+// ------------------------------------------------------------------------------------
+// cell access
+// ------------------------------------------------------------------------------------
+template <int DIM>
+__device__ __forceinline__ int cell_nverts(const CellsView &g, int64_t c, int64_t *first) {
+    if (g.off) { *first = g.off[c]; return g.off[c + 1] - g.off[c]; }
+    *first = c * g.nv;
+    return g.nv;
+}
+
+// signed area of cell c as stored (no orientation fix-up)
+template <int DIM>
+__device__ double cell_signed_area(const CellsView &g, int64_t c) {
+    int64_t f;
+    const int n = cell_nverts<DIM>(g, c, &f);
+    const double *p = g.verts + f * DIM;
+    if (DIM == 3) {
+        ExcessAcc acc;
+        const d3 a = {p[0], p[1], p[2]};
+        d3 b = {p[3], p[4], p[5]};
+        for (int i = 2; i < n; ++i) {
+            const d3 cc = {p[3 * i], p[3 * i + 1], p[3 * i + 2]};
+            acc.add_triangle(a, b, cc);
+            b = cc;
+        }
+        return acc.area();
+    } else {
+        double s = 0.0;
+        const double x0 = p[0], y0 = p[1];
+        for (int i = 1; i + 1 < n; ++i) {
+            const double ax = p[2 * i] - x0, ay = p[2 * i + 1] - y0;
+            const double bx = p[2 * i + 2] - x0, by = p[2 * i + 3] - y0;
+            s += ax * by - ay * bx;
+        }
+        return 0.5 * s;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Sutherland-Hodgman clip + area of one (subject, clip) pair.
+//
+// Shared-memory working polygon: slot v, coordinate c of thread t lives at
+//   buf[((v * DIM) + c) * NT + t]            (NT = threads per block)
+// so a warp touches consecutive doubles -- conflict-free -- and nothing spills to local
+// memory.  MAXW = capacity of the working polygon (subject + clip vertex counts).
+// ------------------------------------------------------------------------------------
+template <int DIM, int NT, int MAXW>
+struct PolyBuf {
+    double *b;   // this thread's column: b[(v*DIM + c) * NT]
+    __device__ __forceinline__ double get(int v, int c) const { return b[(v * DIM + c) * NT]; }
+    __device__ __forceinline__ void set(int v, int c, double x) { b[(v * DIM + c) * NT] = x; }
+};
+
+// Returns the (non-negative up to round-off) area of subject ∩ clip on the unit sphere
+// (DIM == 3) or in the plane (DIM == 2); 0 when the intersection has fewer than 3 vertices.
+template <int DIM, int NT, int MAXW>
+__device__ double clip_pair_area(const CellsView &gs, int64_t s, const CellsView &gc, int64_t c,
+                                 double *smem /* 2 * MAXW * DIM * NT doubles */) {
+    PolyBuf<DIM, NT, MAXW> cur{smem + threadIdx.x};
+    PolyBuf<DIM, NT, MAXW> nxt{smem + MAXW * DIM * NT + threadIdx.x};
+
+    int64_t sf, cf;
+    const int ns = cell_nverts<DIM>(gs, s, &sf);
+    const int nc = cell_nverts<DIM>(gc, c, &cf);
+    const double *sp = gs.verts + sf * DIM;
+    const double *cp = gc.verts + cf * DIM;
+    const bool sflip = gs.flip && gs.flip[s];
+    const bool cflip = gc.flip && gc.flip[c];
+
+    // subject ring -> shared memory, oriented CCW
+    for (int i = 0; i < ns; ++i) {
+        const double *q = sp + (sflip ? (ns - 1 - i) : i) * DIM;
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) cur.set(i, k, q[k]);
+    }
+    int m = ns;
+
+    for (int e = 0; e < nc && m > 0; ++e) {
+        const int iu = cflip ? (nc - 1 - e) : e;
+        const int iv = cflip ? (iu == 0 ? nc - 1 : iu - 1) : (e + 1 == nc ? 0 : e + 1);
+        const double *u = cp + iu * DIM, *v = cp + iv * DIM;
+        // half-space of the directed edge u -> v: inside <=> h(p) >= 0
+        double nx, ny, nz = 0.0, h0 = 0.0;
+        if (DIM == 3) {
+            const d3 n = cross(d3{u[0], u[1], u[2]}, d3{v[0], v[1], v[2]});
+            nx = n.x; ny = n.y; nz = n.z;
+            if (nx == 0.0 && ny == 0.0 && nz == 0.0) continue;   // zero-length edge (pole cells)
+        } else {
+            const double ex = v[0] - u[0], ey = v[1] - u[1];
+            if (ex == 0.0 && ey == 0.0) continue;
+            nx = -ey; ny = ex;                    // h(p) = ex*(py-uy) - ey*(px-ux)
+            h0 = -(nx * u[0] + ny * u[1]);
+        }
+        auto hval = [&](int i) -> double {
+            if (DIM == 3) return fma(nx, cur.get(i, 0), fma(ny, cur.get(i, 1), nz * cur.get(i, 2)));
+            return fma(nx, cur.get(i, 0), fma(ny, cur.get(i, 1), h0));
+        };
+        int mo = 0;
+        double dp = hval(m - 1);
+        double px = cur.get(m - 1, 0), py = cur.get(m - 1, 1), pz = DIM == 3 ? cur.get(m - 1, 2) : 0.0;
+        for (int i = 0; i < m; ++i) {
+            const double qx = cur.get(i, 0), qy = cur.get(i, 1), qz = DIM == 3 ? cur.get(i, 2) : 0.0;
+            const double dq = hval(i);
+            const bool in_p = dp >= 0.0, in_q = dq >= 0.0;
+            if (in_p != in_q) {
+                const double t = dp / (dp - dq);
+                double rx = fma(t, qx - px, px), ry = fma(t, qy - py, py), rz = fma(t, qz - pz, pz);
+                if (DIM == 3) {
+                    const double inv = rsqrt(rx * rx + ry * ry + rz * rz);
+                    rx *= inv; ry *= inv; rz *= inv;
+                }
+                if (mo < MAXW) {
+                    nxt.set(mo, 0, rx); nxt.set(mo, 1, ry);
+                    if (DIM == 3) nxt.set(mo, 2, rz);
+                    ++mo;
+                }
+            }
+            if (in_q && mo < MAXW) {
+                nxt.set(mo, 0, qx); nxt.set(mo, 1, qy);
+                if (DIM == 3) nxt.set(mo, 2, qz);
+                ++mo;
+            }
+            dp = dq; px = qx; py = qy; pz = qz;
+        }
+        m = mo;
+        double *t = cur.b; cur.b = nxt.b; nxt.b = t;
+    }
+    if (m < 3) return 0.0;
+
+    if (DIM == 3) {
+        ExcessAcc acc;
+        const d3 a = {cur.get(0, 0), cur.get(0, 1), cur.get(0, 2)};
+        d3 b = {cur.get(1, 0), cur.get(1, 1), cur.get(1, 2)};
+        for (int i = 2; i < m; ++i) {
+            const d3 cc = {cur.get(i, 0), cur.get(i, 1), cur.get(i, 2)};
+            acc.add_triangle(a, b, cc);
+            b = cc;
+        }
+        return acc.area();
+    } else {
+        double sarea = 0.0;
+        const double x0 = cur.get(0, 0), y0 = cur.get(0, 1);
+        double ax = cur.get(1, 0) - x0, ay = cur.get(1, 1) - y0;
+        for (int i = 2; i < m; ++i) {
+            const double bx = cur.get(i, 0) - x0, by = cur.get(i, 1) - y0;
+            sarea += ax * by - ay * bx;
+            ax = bx; ay = by;
+        }
+        return 0.5 * sarea;
+    }
+}
+
+}  // namespace crg

@@ -1,0 +1,275 @@
+// kernels.cuh -- clip/area kernel, cell areas, COO -> CSR/CSC assembly helpers, normalize,
+// and the apply kernels (CSR SpMV / SpMM with the area division fused in).
+#pragma once
+#include "common.cuh"
+#include "geom.cuh"
+
+namespace crg {
+
+// =======================================================================================
+// K3: one thread per candidate pair -> clip + area; block-aggregated compaction of the
+// pairs with area > threshold into (key = dst << 32 | src, val = area * R^2).
+// Replaces compute_intersection_areas (/root/reference/src/regridder/intersection_areas.jl:4-32).
+// FP64-pipe bound.
+// =======================================================================================
+template <int DIM, int NT, int MAXW>
+__global__ void __launch_bounds__(NT) clip_kernel(CellsView gd, CellsView gs, const int2 *__restrict__ pairs,
+                                                  int64_t npairs, double scale, double thresh,
+                                                  uint64_t *__restrict__ coo_key, double *__restrict__ coo_val,
+                                                  unsigned long long *__restrict__ counter) {
+    extern __shared__ double clip_smem[];
+    __shared__ unsigned int warp_cnt[NT / 32];
+    __shared__ unsigned long long block_base;
+    const int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x;
+    double area = 0.0;
+    int2 pr = make_int2(0, 0);
+    if (idx < npairs) {
+        pr = pairs[idx];
+        area = clip_pair_area<DIM, NT, MAXW>(gs, pr.x, gd, pr.y, clip_smem);
+    }
+    const bool keep = area > thresh;
+    const unsigned mask = __ballot_sync(CRG_FULL, keep);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) warp_cnt[wid] = __popc(mask);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) { unsigned c = warp_cnt[w]; warp_cnt[w] = tot; tot += c; }
+        block_base = tot ? atomicAdd(counter, (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
+    if (keep) {
+        const unsigned long long pos = block_base + warp_cnt[wid] + __popc(mask & ((1u << lane) - 1u));
+        coo_key[pos] = ((uint64_t)(uint32_t)pr.y << 32) | (uint32_t)pr.x;
+        coo_val[pos] = area * scale;
+    }
+}
+
+// =======================================================================================
+// K4: per-cell geometric area (regridder.jl:165-178) + orientation flags.
+// =======================================================================================
+template <int DIM>
+__global__ void __launch_bounds__(256) cell_area_kernel(CellsView g, double scale, double *__restrict__ areas,
+                                                        uint8_t *__restrict__ flip, unsigned int *__restrict__ nflip) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= g.ncells) return;
+    const double a = cell_signed_area<DIM>(g, c);
+    areas[c] = fabs(a) * scale;
+    const bool f = a < 0.0;
+    flip[c] = f ? 1 : 0;
+    if (f) atomicAdd(nflip, 1u);
+}
+
+// =======================================================================================
+// K5 helpers: duplicate summation, key swap, CSR split.
+// =======================================================================================
+__global__ void __launch_bounds__(256) mark_heads_kernel(const uint64_t *__restrict__ keys, int64_t n,
+                                                         uint32_t *__restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+
+// heads_pos = exclusive scan of the head flags.  Every head sums its run (segmented reduce).
+__global__ void __launch_bounds__(256) dedupe_kernel(const uint64_t *__restrict__ keys, const double *__restrict__ vals,
+                                                     const uint32_t *__restrict__ flags,
+                                                     const uint32_t *__restrict__ heads_pos, int64_t n,
+                                                     uint64_t *__restrict__ okeys, double *__restrict__ ovals) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flags[i]) return;
+    double s = vals[i];
+    for (int64_t j = i + 1; j < n && !flags[j]; ++j) s += vals[j];
+    okeys[heads_pos[i]] = keys[i];
+    ovals[heads_pos[i]] = s;
+}
+
+__global__ void __launch_bounds__(256) swap_key_kernel(const uint64_t *__restrict__ in, int64_t n,
+                                                       uint64_t *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const uint64_t k = in[i]; out[i] = (k << 32) | (k >> 32); }
+}
+
+// keys sorted by (row << 32 | col): write col indices, values and the row pointer array.
+__global__ void __launch_bounds__(256) split_csr_kernel(const uint64_t *__restrict__ keys,
+                                                        const double *__restrict__ vals, int64_t nnz,
+                                                        int64_t n_rows, int32_t *__restrict__ rowptr,
+                                                        int32_t *__restrict__ colidx, double *__restrict__ ovals) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnz) return;
+    const uint64_t k = keys[i];
+    const int64_t r = (int64_t)(k >> 32);
+    colidx[i] = (int32_t)(uint32_t)k;
+    ovals[i] = vals[i];
+    const int64_t rprev = i == 0 ? -1 : (int64_t)(keys[i - 1] >> 32);
+    for (int64_t rr = rprev + 1; rr <= r; ++rr) rowptr[rr] = (int32_t)i;
+    if (i == nnz - 1)
+        for (int64_t rr = r + 1; rr <= n_rows; ++rr) rowptr[rr] = (int32_t)nnz;
+}
+
+__global__ void __launch_bounds__(256) fill_i32_kernel(int32_t *p, int64_t n, int32_t v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// (dst, src, area) int64/double triples -> packed keys
+__global__ void __launch_bounds__(256) pack_coo_kernel(const int64_t *__restrict__ rows, const int64_t *__restrict__ cols,
+                                                       int64_t n, uint64_t *__restrict__ keys) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = ((uint64_t)(uint32_t)rows[i] << 32) | (uint32_t)cols[i];
+}
+
+// =======================================================================================
+// K6: normalize!  (regridder.jl:54-62)
+// =======================================================================================
+__global__ void __launch_bounds__(256) max_kernel(const double *__restrict__ v, int64_t n, double *out) {
+    double m = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmax(m, v[i]);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0 && m > 0.0) atomic_max_pos_double(out, m);
+}
+__global__ void __launch_bounds__(256) div_by_kernel(double *__restrict__ v, int64_t n, const double *__restrict__ m) {
+    const double d = *m;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        v[i] = v[i] / d;
+}
+
+// =======================================================================================
+// K7: CSR SpMV, y = A x (./ areas).  One warp per 32 consecutive rows: the warp streams the
+// rows' contiguous nnz range in coalesced 256-element chunks (val * x[col] staged in shared
+// memory), and each lane sums the part of the chunk that belongs to its own row, in column
+// order.  A chunk lying entirely inside one (long) row is reduced cooperatively instead.
+// Replaces mul! + the separate `dst ./= dst_areas` pass (regrid.jl:95-118).  HBM-bound:
+// 12 B/nnz + 4 B/row pointer + 8 B/row area + 8 B/row output + the x gather.
+// =======================================================================================
+constexpr int SPMV_THREADS = 256;
+constexpr int SPMV_CHUNK = 256;
+__device__ __forceinline__ int spmv_skew(int i) { return i + (i >> 3); }
+
+template <bool DIVIDE>
+__global__ void __launch_bounds__(SPMV_THREADS) spmv_kernel(const int32_t *__restrict__ rowptr,
+                                                            const int32_t *__restrict__ colidx,
+                                                            const double *__restrict__ vals,
+                                                            const double *__restrict__ x, double *__restrict__ y,
+                                                            const double *__restrict__ areas, int64_t n_rows) {
+    __shared__ double sbuf[SPMV_THREADS / 32][SPMV_CHUNK + SPMV_CHUNK / 8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t r0 = ((int64_t)blockIdx.x * (SPMV_THREADS / 32) + wid) * 32;
+    if (r0 >= n_rows) return;
+    const int64_t r = r0 + lane;
+    const int a = rowptr[r < n_rows ? r : n_rows];
+    const int b = rowptr[r + 1 < n_rows ? r + 1 : n_rows];
+    const int start = __shfl_sync(CRG_FULL, a, 0), end = __shfl_sync(CRG_FULL, b, 31);
+    double *sb = sbuf[wid];
+    double acc = 0.0;
+    for (int c0 = start; c0 < end; c0 += SPMV_CHUNK) {
+        const int cend = min(c0 + SPMV_CHUNK, end);
+        double p[SPMV_CHUNK / 32];
+#pragma unroll
+        for (int u = 0; u < SPMV_CHUNK / 32; ++u) {
+            const int idx = c0 + u * 32 + lane;
+            p[u] = idx < end ? vals[idx] * __ldg(&x[colidx[idx]]) : 0.0;
+        }
+        const unsigned owner = __ballot_sync(CRG_FULL, a <= c0 && b >= cend && b > a);
+        if (owner) {   // whole chunk inside one row: cooperative reduction
+            double s = 0.0;
+#pragma unroll
+            for (int u = 0; u < SPMV_CHUNK / 32; ++u) s += p[u];
+            s = warp_sum(s);
+            if (lane == __ffs(owner) - 1) acc += s;
+            continue;
+        }
+#pragma unroll
+        for (int u = 0; u < SPMV_CHUNK / 32; ++u) sb[spmv_skew(u * 32 + lane)] = p[u];
+        __syncwarp();
+        const int lo = max(a, c0) - c0, hi = min(b, cend) - c0;
+        for (int k = lo; k < hi; ++k) acc += sb[spmv_skew(k)];
+        __syncwarp();
+    }
+    if (r < n_rows) y[r] = DIVIDE ? acc / areas[r] : acc;
+}
+
+// =======================================================================================
+// K8a: CSR SpMM, level-fastest layout x[cell * ldx + k]: one warp per row, lanes across the
+// K levels (coalesced 8*K-byte reads of each gathered source row, L2-resident reuse).
+// Replaces the NDSliceLoop of K sequential SpMVs (regrid.jl:303-318).
+// =======================================================================================
+template <int KT, bool DIVIDE>
+__global__ void __launch_bounds__(256) spmm_lf_kernel(const int32_t *__restrict__ rowptr,
+                                                      const int32_t *__restrict__ colidx,
+                                                      const double *__restrict__ vals, const double *__restrict__ x,
+                                                      double *__restrict__ y, const double *__restrict__ areas,
+                                                      int64_t n_rows, int64_t K, int64_t ldx, int64_t ldy) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n_rows) return;
+    const int a = rowptr[r], b = rowptr[r + 1];
+    const double inv_area_num = DIVIDE ? areas[r] : 1.0;
+    for (int64_t kb = 0; kb < K; kb += 32 * KT) {
+        double acc[KT];
+#pragma unroll
+        for (int t = 0; t < KT; ++t) acc[t] = 0.0;
+#pragma unroll 4
+        for (int j = a; j < b; ++j) {
+            const double v = vals[j];
+            const double *xp = x + (int64_t)colidx[j] * ldx + kb;
+#pragma unroll
+            for (int t = 0; t < KT; ++t) {
+                const int64_t k = t * 32 + lane;
+                if (kb + k < K) acc[t] += v * __ldg(&xp[k]);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < KT; ++t) {
+            const int64_t k = kb + t * 32 + lane;
+            if (k < K) y[r * ldy + k] = DIVIDE ? acc[t] / inv_area_num : acc[t];
+        }
+    }
+}
+
+// =======================================================================================
+// K8b: CSR SpMM, cell-fastest layout x[k * ldx + cell] (Julia dims = 1): one thread per row,
+// KC levels per thread so the row's (col, val) are read once per KC levels; output writes
+// are coalesced across rows.
+// =======================================================================================
+template <int KC, bool DIVIDE>
+__global__ void __launch_bounds__(128) spmm_cf_kernel(const int32_t *__restrict__ rowptr,
+                                                      const int32_t *__restrict__ colidx,
+                                                      const double *__restrict__ vals, const double *__restrict__ x,
+                                                      double *__restrict__ y, const double *__restrict__ areas,
+                                                      int64_t n_rows, int64_t K, int64_t ldx, int64_t ldy) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t k0 = (int64_t)blockIdx.y * KC;
+    if (r >= n_rows) return;
+    const int a = rowptr[r], b = rowptr[r + 1];
+    double acc[KC];
+#pragma unroll
+    for (int t = 0; t < KC; ++t) acc[t] = 0.0;
+    for (int j = a; j < b; ++j) {
+        const double v = vals[j];
+        const double *xp = x + colidx[j] + k0 * ldx;
+#pragma unroll
+        for (int t = 0; t < KC; ++t)
+            if (k0 + t < K) acc[t] += v * __ldg(&xp[t * ldx]);
+    }
+    const double ar = DIVIDE ? areas[r] : 1.0;
+#pragma unroll
+    for (int t = 0; t < KC; ++t)
+        if (k0 + t < K) y[(k0 + t) * ldy + r] = DIVIDE ? acc[t] / ar : acc[t];
+}
+
+// =======================================================================================
+// FP64 FMA throughput micro-benchmark (roofline denominator of the clip kernel)
+// =======================================================================================
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace crg

@@ -1,0 +1,513 @@
+"""Python mirror of the reference's public API for the two hot paths, on top of the C ABI.
+
+=====================================  ====================================================
+reference (Julia)                      here
+=====================================  ====================================================
+``Regridder(dst, src; normalize, …)``  :func:`Regridder` / :class:`RegridderB200`
+                                       (src/regridder/regridder.jl:105-163)
+``regrid!(dst, R, src; dims, …)``      :func:`regrid_` (src/regridder/regrid.jl:63-118,205-318)
+``regrid(R, src)``                     :func:`regrid`  (regrid.jl:322-330)
+``transpose(R)``                       :func:`transpose` / ``R.T`` (regridder.jl:49-50) -- shares
+                                       every array with ``R`` (``is``), flips a flag
+``LinearAlgebra.normalize!(R)``        :func:`normalize_` (regridder.jl:54-62)
+``R.intersections``                    :class:`B200Matrix` (device CSR(A) + CSR(A^T) handle)
+``R.dst_areas / R.src_areas``          numpy vectors (geometric cell areas, regridder.jl:165-178)
+``R.dst_temp / R.src_temp``            numpy work vectors for non-contiguous fields (:155-156)
+=====================================  ====================================================
+
+Julia is not installed in this image, so this module is the executable host side; the
+``ccall`` binding a Julia maintainer would add is in INTEGRATION.md / julia/CRGB200.jl.
+Fields may be numpy arrays (host; copied through the device inside the call) or CUDA
+``torch`` tensors (device; zero-copy).  Indices are 0-based here, ``dims`` is the 0-based
+axis (the reference's ``dims`` is 1-based; ``dims=0`` here == ``dims=1`` there).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Optional
+
+import numpy as np
+
+from . import _lib
+from .grids import Grid, PLANAR, SPHERICAL, cells_from_vertex_matrix, planar_regular_grid, polygons_grid
+
+
+class DimensionMismatch(ValueError):
+    """Julia's ``DimensionMismatch`` (regrid.jl:285-298)."""
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
+
+
+# -----------------------------------------------------------------------------------------
+# Trees.treeify equivalent: anything -> flat cell list in field-linear order
+# -----------------------------------------------------------------------------------------
+
+def as_grid(obj, manifold: Optional[int] = None, radius: float = 1.0) -> Grid:
+    """``Trees.treeify(manifold, x)`` + ``collect(getcell(tree))`` (src/trees/interfaces.jl:94-129).
+
+    Accepts a :class:`Grid`; an ``(x, y)`` tuple of 1-D vectors (``RegularGrid``, planar); an
+    ``(nx+1, ny+1, dim)`` array of corner points (``CellBasedGrid``); an ``(nx, ny)`` object array /
+    nested list of polygons; or a flat iterable of polygons (``FlatNoTree``)."""
+    if isinstance(obj, Grid):
+        return obj
+    if isinstance(obj, tuple) and len(obj) == 2 and np.ndim(obj[0]) == 1 and np.ndim(obj[1]) == 1 \
+            and np.asarray(obj[0]).dtype.kind in "fiu":
+        return planar_regular_grid(obj[0], obj[1])
+    if isinstance(obj, np.ndarray) and obj.dtype.kind == "f" and obj.ndim == 3 and obj.shape[2] in (2, 3):
+        mf = SPHERICAL if obj.shape[2] == 3 else PLANAR
+        return Grid(cells_from_vertex_matrix(obj.astype(np.float64)), mf, None, radius, "cellbased")
+    if isinstance(obj, np.ndarray) and obj.dtype == object and obj.ndim == 2:
+        # matrix of polygons: linear index i + j*nx (column-major, interfaces.jl:236-243)
+        polys = [obj[i, j] for j in range(obj.shape[1]) for i in range(obj.shape[0])]
+        return polygons_grid(polys, PLANAR if manifold is None else manifold, radius)
+    polys = list(obj)
+    if not polys:
+        raise TypeError("cannot treeify an empty iterable")
+    dim = np.asarray(polys[0]).shape[-1]
+    mf = manifold if manifold is not None else (SPHERICAL if dim == 3 else PLANAR)
+    return polygons_grid(polys, mf, radius)
+
+
+def _cells_struct(g: Grid, keep: list) -> _lib.Cells:
+    c = _lib.Cells()
+    v = g.verts
+    if _is_torch(v):
+        keep.append(v)
+        c.verts = v.data_ptr()
+    else:
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        keep.append(v)
+        c.verts = v.ctypes.data
+    if g.offsets is not None:
+        o = g.offsets
+        if _is_torch(o):
+            keep.append(o)
+            c.offsets = o.data_ptr()
+        else:
+            o = np.ascontiguousarray(o, dtype=np.int32)
+            keep.append(o)
+            c.offsets = o.ctypes.data
+        c.nv = 0
+    else:
+        c.offsets = None
+        c.nv = g.nv
+    c.ncells = g.ncells
+    return c
+
+
+# -----------------------------------------------------------------------------------------
+# the matrix handle
+# -----------------------------------------------------------------------------------------
+
+class _Handle:
+    """Owns one ``crg_regridder*``; freed with the last reference (Julia finalizer analogue)."""
+
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _lib.lib().crg_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class B200Matrix:
+    """``R.intersections``: n_dst x n_src sparse matrix living on the device.  ``transpose`` is a
+    flag flip over the same handle (regridder.jl:49-50)."""
+
+    def __init__(self, handle: _Handle, n_dst: int, n_src: int, transposed: bool = False):
+        self._h = handle
+        self._n_dst = n_dst
+        self._n_src = n_src
+        self.transposed = transposed
+
+    @property
+    def shape(self):
+        return (self._n_src, self._n_dst) if self.transposed else (self._n_dst, self._n_src)
+
+    @property
+    def nnz(self) -> int:
+        nnz = C.c_int64()
+        _lib.check(_lib.lib().crg_dims(self._h.ptr, None, None, C.byref(nnz)))
+        return int(nnz.value)
+
+    @property
+    def T(self):
+        return B200Matrix(self._h, self._n_dst, self._n_src, not self.transposed)
+
+    def transpose(self):
+        return self.T
+
+    def tocsc(self):
+        """``SparseMatrixCSC`` of this (possibly transposed) matrix as a scipy matrix."""
+        import scipy.sparse as sp
+        nnz = self.nnz
+        colptr = np.empty(self._n_src + 1, dtype=np.int64)
+        rowval = np.empty(nnz, dtype=np.int64)
+        nzval = np.empty(nnz, dtype=np.float64)
+        _lib.check(_lib.lib().crg_export_csc(self._h.ptr, 0, colptr.ctypes.data, rowval.ctypes.data,
+                                             nzval.ctypes.data))
+        A = sp.csc_matrix((nzval, rowval, colptr), shape=(self._n_dst, self._n_src))
+        return A.T.tocsc() if self.transposed else A
+
+    def tocsr(self):
+        import scipy.sparse as sp
+        nnz = self.nnz
+        rowptr = np.empty(self._n_dst + 1, dtype=np.int64)
+        colval = np.empty(nnz, dtype=np.int64)
+        nzval = np.empty(nnz, dtype=np.float64)
+        _lib.check(_lib.lib().crg_export_csr(self._h.ptr, 0, rowptr.ctypes.data, colval.ctypes.data,
+                                             nzval.ctypes.data))
+        A = sp.csr_matrix((nzval, colval, rowptr), shape=(self._n_dst, self._n_src))
+        return A.T.tocsr() if self.transposed else A
+
+    def findnz(self):
+        """``SparseArrays.findnz`` (column-major order), 0-based."""
+        A = self.tocsc().tocoo()
+        return A.row, A.col, A.data
+
+    def toarray(self):
+        return self.tocsc().toarray()
+
+    def maximum(self) -> float:
+        A = self.tocsc()
+        return float(A.data.max()) if A.nnz else 0.0
+
+    def stats(self) -> dict:
+        s = _lib.BuildStats()
+        _lib.check(_lib.lib().crg_stats(self._h.ptr, C.byref(s)))
+        return s.asdict()
+
+    def candidates(self):
+        n = self.stats()["n_candidates"]
+        s = np.empty(n, dtype=np.int64)
+        d = np.empty(n, dtype=np.int64)
+        _lib.check(_lib.lib().crg_candidates(self._h.ptr, s.ctypes.data, d.ctypes.data))
+        return s, d
+
+    def set_stream(self, cuda_stream_ptr: int):
+        _lib.check(_lib.lib().crg_set_stream(self._h.ptr, C.c_void_p(cuda_stream_ptr or None)))
+
+    def synchronize(self):
+        _lib.check(_lib.lib().crg_synchronize(self._h.ptr))
+
+    def apply_bytes(self, K: int = 1, divide: bool = True) -> int:
+        b = C.c_int64()
+        _lib.check(_lib.lib().crg_apply_bytes(self._h.ptr, int(self.transposed), int(divide), K, C.byref(b)))
+        return int(b.value)
+
+    # y = M x (./ areas) -- the fused perform_regridding! + finalize_regridding!
+    def apply(self, dst_ptr: int, src_ptr: int, K: int, ld_dst: int, ld_src: int, level_fastest: bool,
+              divide: bool, asynchronous: bool = False):
+        f = _lib.lib().crg_apply_async if asynchronous else _lib.lib().crg_apply
+        _lib.check(f(self._h.ptr, int(self.transposed), int(divide), C.c_void_p(dst_ptr), C.c_void_p(src_ptr),
+                     K, ld_dst, ld_src, int(level_fastest)))
+
+
+# -----------------------------------------------------------------------------------------
+# Regridder
+# -----------------------------------------------------------------------------------------
+
+class RegridderB200:
+    """``Regridder{W,A,V}`` (regridder.jl:25-36)."""
+
+    def __init__(self, intersections: B200Matrix, dst_areas, src_areas, dst_temp, src_temp):
+        self.intersections = intersections
+        self.dst_areas = dst_areas
+        self.src_areas = src_areas
+        self.dst_temp = dst_temp
+        self.src_temp = src_temp
+
+    @property
+    def shape(self):
+        return self.intersections.shape
+
+    def size(self, dim: Optional[int] = None):
+        return self.shape if dim is None else self.shape[dim]
+
+    @property
+    def T(self):
+        return transpose(self)
+
+    def __repr__(self):
+        n2, n1 = self.shape
+        return f"{n2}x{n1} RegridderB200(nnz={self.intersections.nnz})"
+
+
+def transpose(R: RegridderB200) -> RegridderB200:
+    """``LinearAlgebra.transpose(::Regridder)``: no copy, areas and temps swapped (regridder.jl:49-50)."""
+    return RegridderB200(R.intersections.T, R.src_areas, R.dst_areas, R.src_temp, R.dst_temp)
+
+
+def _refresh_areas(R: RegridderB200):
+    M = R.intersections
+    da = R.src_areas if M.transposed else R.dst_areas
+    sa = R.dst_areas if M.transposed else R.src_areas
+    _lib.check(_lib.lib().crg_areas(M._h.ptr, da.ctypes.data, sa.ctypes.data))
+
+
+def normalize_(R: RegridderB200) -> RegridderB200:
+    """``LinearAlgebra.normalize!(R)``: divide A and both area vectors by maximum(A)."""
+    _lib.check(_lib.lib().crg_normalize(R.intersections._h.ptr))
+    _refresh_areas(R)
+    return R
+
+
+def _make_options(manifold, normalize, radius, device, area_threshold, build_transpose, keep_candidates):
+    o = _lib.Options()
+    _lib.check(_lib.lib().crg_options_init(C.byref(o)))
+    o.manifold = manifold
+    o.normalize = int(bool(normalize))
+    o.radius = float(radius)
+    o.device = -1 if device is None else int(device)
+    o.area_threshold = float(area_threshold)
+    o.build_transpose = int(bool(build_transpose))
+    o.keep_candidates = int(bool(keep_candidates))
+    return o
+
+
+def _wrap(ptr, n_dst, n_src) -> RegridderB200:
+    h = _Handle(ptr)
+    M = B200Matrix(h, n_dst, n_src)
+    da = np.empty(n_dst)
+    sa = np.empty(n_src)
+    _lib.check(_lib.lib().crg_areas(ptr, da.ctypes.data, sa.ctypes.data))
+    return RegridderB200(M, da, sa, np.zeros(n_dst), np.zeros(n_src))
+
+
+def Regridder(dst, src, *, manifold: Optional[int] = None, normalize: bool = False,
+              intersection_operator: Optional[Callable] = None, threaded=True, radius: Optional[float] = None,
+              device: Optional[int] = None, area_threshold: float = 0.0, build_transpose: bool = True,
+              keep_candidates: bool = False, **_ignored) -> RegridderB200:
+    """``Regridder(dst, src; normalize=false, intersection_operator, threaded, …)``
+    (regridder.jl:105-163).  ``threaded`` is accepted and ignored (the device is the parallelism);
+    a custom ``intersection_operator(src_polygon, dst_polygon) -> area`` is evaluated on the host for
+    every candidate pair of the device broad phase and assembled on the device
+    (intersection_areas.jl:20-27)."""
+    gd = as_grid(dst, manifold)
+    gs = as_grid(src, manifold)
+    if gd.manifold != gs.manifold:
+        raise ValueError(f"Destination and source manifolds must be the same. Got {gd.manifold} and {gs.manifold}.")
+    mf = gd.manifold
+    if radius is None:
+        radius = gd.radius
+    keep = []
+    cd = _cells_struct(gd, keep)
+    cs = _cells_struct(gs, keep)
+    L = _lib.lib()
+    out = C.c_void_p()
+    if intersection_operator is None:
+        o = _make_options(mf, normalize, radius, device, area_threshold, build_transpose, keep_candidates)
+        _lib.check(L.crg_build(C.byref(o), C.byref(cd), C.byref(cs), C.byref(out)))
+        return _wrap(out.value, gd.ncells, gs.ncells)
+    # plugin path: device broad phase -> host operator per pair -> device assembly
+    o = _make_options(mf, False, radius, device, 0.0, False, True)
+    _lib.check(L.crg_build(C.byref(o), C.byref(cd), C.byref(cs), C.byref(out)))
+    tmp = _wrap(out.value, gd.ncells, gs.ncells)
+    ps, pd = tmp.intersections.candidates()
+    order = np.lexsort((ps, pd))
+    ps, pd = ps[order], pd[order]
+    rows, cols, vals = [], [], []
+    for s, d in zip(ps.tolist(), pd.tolist()):
+        a = float(intersection_operator(np.asarray(gs.cell(s)), np.asarray(gd.cell(d))))
+        if a > 0:
+            rows.append(d); cols.append(s); vals.append(a)
+    rows = np.asarray(rows, dtype=np.int64)
+    cols = np.asarray(cols, dtype=np.int64)
+    vals = np.asarray(vals, dtype=np.float64)
+    o2 = _make_options(mf, normalize, radius, device, 0.0, build_transpose, False)
+    out2 = C.c_void_p()
+    _lib.check(L.crg_build_from_coo(C.byref(o2), gd.ncells, gs.ncells, len(vals), rows.ctypes.data, cols.ctypes.data,
+                                    vals.ctypes.data, tmp.dst_areas.ctypes.data, tmp.src_areas.ctypes.data,
+                                    C.byref(out2)))
+    return _wrap(out2.value, gd.ncells, gs.ncells)
+
+
+def regridder_from_coo(n_dst, n_src, dst_idx, src_idx, areas, dst_areas, src_areas, *, normalize=False,
+                       device=None, manifold=SPHERICAL) -> RegridderB200:
+    """``SparseArrays.sparse(i2s, i1s, areas, n_dst, n_src)`` wrapped into a Regridder
+    (intersection_areas.jl:115-121): duplicates are summed."""
+    r = np.ascontiguousarray(dst_idx, dtype=np.int64)
+    c = np.ascontiguousarray(src_idx, dtype=np.int64)
+    v = np.ascontiguousarray(areas, dtype=np.float64)
+    da = np.ascontiguousarray(dst_areas, dtype=np.float64)
+    sa = np.ascontiguousarray(src_areas, dtype=np.float64)
+    o = _make_options(manifold, normalize, 1.0, device, 0.0, True, False)
+    out = C.c_void_p()
+    _lib.check(_lib.lib().crg_build_from_coo(C.byref(o), n_dst, n_src, len(v), r.ctypes.data, c.ctypes.data,
+                                             v.ctypes.data, da.ctypes.data, sa.ctypes.data, C.byref(out)))
+    return _wrap(out.value, n_dst, n_src)
+
+
+# -----------------------------------------------------------------------------------------
+# regrid!
+# -----------------------------------------------------------------------------------------
+
+def _layout(arr, ax: int, n: int):
+    """Describe an N-D field as K vectors of n cells for crg_apply without copying if possible.
+    Returns (K, ld, level_fastest) or None when the memory is not expressible."""
+    if _is_torch(arr):
+        shape, strides = tuple(arr.shape), tuple(arr.stride())
+    else:
+        shape, strides = arr.shape, tuple(s // arr.itemsize for s in arr.strides)
+    K = 1
+    for i, s in enumerate(shape):
+        if i != ax:
+            K *= s
+    if K == 1:
+        return (1, n, False) if (strides[ax] == 1 or n <= 1) else None
+    # the non-spatial axes, in C order, must collapse into one index with a single stride
+    other = [(shape[i], strides[i]) for i in range(len(shape)) if i != ax and shape[i] > 1]
+    if not other:
+        return (1, n, False) if strides[ax] == 1 else None
+    base = other[-1][1]
+    run = base
+    for sz, st in reversed(other):
+        if st != run:
+            return None
+        run *= sz
+    if strides[ax] == 1 and base >= n:          # each level contiguous, levels `base` apart
+        return (K, base, False)
+    if base == 1 and strides[ax] >= K:          # levels contiguous per cell
+        return (K, strides[ax], True)
+    return None
+
+
+def _ptr(a) -> int:
+    return a.data_ptr() if _is_torch(a) else a.ctypes.data
+
+
+def regrid_(dst_field, R: RegridderB200, src_field, *, dims: int = 0, normalize: bool = True,
+            asynchronous: bool = False):
+    """``regrid!(dst_field, regridder, src_field; dims, normalize)`` (regrid.jl:63-118,205-318).
+
+    1-D dense fields go straight to the device kernel; 1-D strided views are staged through
+    ``R.src_temp`` / ``R.dst_temp`` exactly like the reference; N-D arrays are regridded along axis
+    ``dims`` for all other indices in ONE batched SpMM launch (the reference loops K SpMVs)."""
+    for f in (dst_field, src_field):
+        if not (isinstance(f, np.ndarray) or _is_torch(f)):
+            raise TypeError(f"no method matching extract_arraylike(::{type(f).__name__}); "
+                            "fields must be numpy arrays or CUDA torch tensors")
+    M = R.intersections
+    n_out, n_in = M.shape
+    nd_s, nd_d = src_field.ndim, dst_field.ndim
+    if nd_s == 1 and nd_d == 1:
+        if src_field.shape[0] != n_in or dst_field.shape[0] != n_out:
+            raise DimensionMismatch(f"regridder is {n_out}x{n_in}, fields have {dst_field.shape[0]} and {src_field.shape[0]} cells")
+        return _regrid_1d(dst_field, R, src_field, normalize, asynchronous)
+    # ---- NDSliceLoop semantics ----
+    if not (isinstance(dims, (int, np.integer)) and 0 <= dims < nd_s):
+        raise ValueError(f"dims={dims} is out of range for a {nd_s}-dimensional array")
+    if not (0 <= dims < nd_d):
+        raise ValueError(f"dims={dims} is out of range for a {nd_d}-dimensional array")
+    if nd_s != nd_d:
+        raise DimensionMismatch(f"source and destination ranks must match; got source rank {nd_s} and destination rank {nd_d}")
+    s_other = tuple(s for i, s in enumerate(src_field.shape) if i != dims)
+    d_other = tuple(s for i, s in enumerate(dst_field.shape) if i != dims)
+    if s_other != d_other:
+        raise DimensionMismatch(f"source and destination non-spatial axes must match; got source axes {s_other} and destination axes {d_other}")
+    if src_field.shape[dims] != n_in or dst_field.shape[dims] != n_out:
+        raise DimensionMismatch(f"regridder is {n_out}x{n_in}, spatial axes have {dst_field.shape[dims]} and {src_field.shape[dims]} cells")
+    ls = _layout(src_field, dims, n_in)
+    ld = _layout(dst_field, dims, n_out)
+    src_use, dst_use, copy_back = src_field, dst_field, False
+    if _is_torch(src_field) != _is_torch(dst_field):
+        raise TypeError("source and destination fields must both be numpy arrays or both CUDA tensors")
+    if ls is None or ld is None or ls[2] != ld[2] or src_field.dtype != _f64_dtype(src_field) \
+            or dst_field.dtype != _f64_dtype(dst_field):
+        # general strided / non-Float64 case: stage through dense (K, n) Float64 copies
+        src_use = _dense_levels(src_field, dims)
+        dst_use = _empty_like_levels(dst_field, dims)
+        ls = (src_use.shape[0], n_in, False)
+        ld = (dst_use.shape[0], n_out, False)
+        copy_back = True
+    K = ls[0]
+    if K > 0 and n_out > 0:
+        M.apply(_ptr(dst_use), _ptr(src_use), K, ld[1], ls[1], ls[2], normalize, asynchronous and not copy_back)
+    if copy_back:
+        _scatter_levels(dst_field, dst_use, dims)
+    return dst_field
+
+
+def _f64_dtype(a):
+    if _is_torch(a):
+        import torch
+        return torch.float64
+    return np.dtype(np.float64)
+
+
+def _dense_levels(a, ax):
+    if _is_torch(a):
+        import torch
+        return a.movedim(ax, -1).reshape(-1, a.shape[ax]).to(torch.float64).contiguous()
+    return np.ascontiguousarray(np.moveaxis(a, ax, -1).reshape(-1, a.shape[ax]), dtype=np.float64)
+
+
+def _empty_like_levels(a, ax):
+    K = 1
+    for i, s in enumerate(a.shape):
+        if i != ax:
+            K *= s
+    if _is_torch(a):
+        import torch
+        return torch.empty((K, a.shape[ax]), dtype=torch.float64, device=a.device)
+    return np.empty((K, a.shape[ax]), dtype=np.float64)
+
+
+def _scatter_levels(dst, dense, ax):
+    if _is_torch(dst):
+        view = dst.movedim(ax, -1)
+        view.copy_(dense.reshape(view.shape).to(dst.dtype))
+    else:
+        view = np.moveaxis(dst, ax, -1)
+        view[...] = dense.reshape(view.shape)
+
+
+def _regrid_1d(dst, R, src, normalize, asynchronous):
+    M = R.intersections
+    n_out, n_in = M.shape
+    if _is_torch(src) or _is_torch(dst):
+        if not (_is_torch(src) and _is_torch(dst)):
+            raise TypeError("source and destination fields must both be numpy arrays or both CUDA tensors")
+        import torch
+        s = src if (src.is_contiguous() and src.dtype == torch.float64) else src.to(torch.float64).contiguous()
+        d = dst if (dst.is_contiguous() and dst.dtype == torch.float64) else torch.empty(n_out, dtype=torch.float64, device=dst.device)
+        M.apply(d.data_ptr(), s.data_ptr(), 1, n_out, n_in, False, normalize, asynchronous and d is dst)
+        if d is not dst:
+            dst.copy_(d.to(dst.dtype))
+        return dst
+    # extract_source_arraylike / extract_dest_arraylike (regrid.jl:75-79,137-138,273-274)
+    dense_s = src.strides[0] == src.itemsize and src.dtype == np.float64
+    dense_d = dst.strides[0] == dst.itemsize and dst.dtype == np.float64
+    s_like = src if dense_s else R.src_temp
+    d_like = dst if dense_d else R.dst_temp
+    if not dense_s:
+        s_like[:] = src                      # initialize_regridding! (regrid.jl:85-88)
+    M.apply(d_like.ctypes.data, s_like.ctypes.data, 1, n_out, n_in, False, normalize)
+    if not dense_d:
+        dst[:] = d_like                      # finalize_regridding! (regrid.jl:104-111); divide already fused
+    return dst
+
+
+def regrid(R: RegridderB200, src_field, **kw):
+    """``regrid(regridder, src_field)``: allocates the destination (regrid.jl:322-330)."""
+    n_out, _ = R.shape
+    if _is_torch(src_field):
+        import torch
+        dst = torch.zeros(n_out, dtype=src_field.dtype, device=src_field.device)
+    else:
+        dst = np.zeros(n_out, dtype=np.result_type(src_field.dtype, np.float64))
+    return regrid_(dst, R, src_field, **kw)
+
+
+def areas(grid, manifold: Optional[int] = None) -> np.ndarray:
+    """``areas(manifold, x, tree)`` for one grid (regridder.jl:165-178), computed on the device."""
+    g = as_grid(grid, manifold)
+    tiny = Grid(g.verts[:1] if g.offsets is None else g.cell(0)[None], g.manifold, None, g.radius)
+    R = Regridder(g, tiny, build_transpose=False)
+    return R.dst_areas
