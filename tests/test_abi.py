@@ -1,0 +1,76 @@
+"""CPU tests: the C-ABI library loads, exports every symbol include/crg_b200.h declares, and
+fails loudly (no CPU fallback) when there is no CUDA device.  No compute without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from crg_b200 import _lib, grids
+
+HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "crg_b200.h")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(crg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    assert declared_functions() == sorted(_lib.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    for name in declared_functions():
+        assert hasattr(L, name), name
+    assert b"sm_100a" in L.crg_version()
+
+
+def test_struct_layouts_match_header():
+    # sizes follow from the field lists in the header (natural alignment)
+    assert C.sizeof(_lib.Options) == 40
+    assert C.sizeof(_lib.Cells) == 32
+    o = _lib.Options()
+    _lib.check(_lib.lib().crg_options_init(C.byref(o)))
+    assert (o.manifold, o.normalize, o.radius, o.area_threshold, o.device, o.build_transpose) == (1, 0, 1.0, 0.0, -1, 1)
+
+
+def test_argument_validation_needs_no_device():
+    L = _lib.lib()
+    out = C.c_void_p()
+    o = _lib.Options()
+    L.crg_options_init(C.byref(o))
+    assert L.crg_build(None, None, None, C.byref(out)) == _lib.CRG_ERR_INVALID
+    c = _lib.Cells()
+    v = np.zeros((2, 2, 3))
+    c.verts, c.offsets, c.ncells, c.nv = v.ctypes.data, None, 2, 2      # nv = 2 is not a polygon
+    assert L.crg_build(C.byref(o), C.byref(c), C.byref(c), C.byref(out)) == _lib.CRG_ERR_UNSUPPORTED
+    assert b"nv=2" in L.crg_last_error()
+    o.manifold = 7
+    assert L.crg_build(C.byref(o), C.byref(c), C.byref(c), C.byref(out)) == _lib.CRG_ERR_INVALID
+    assert L.crg_dims(None, None, None, None) == _lib.CRG_ERR_INVALID
+    assert L.crg_apply(None, 0, 1, None, None, 1, 0, 0, 0) == _lib.CRG_ERR_INVALID
+
+
+def test_no_cpu_fallback():
+    """Without a device the product path must refuse to compute (never route to the oracle)."""
+    if _lib.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    from crg_b200.regridder import Regridder
+    with pytest.raises(_lib.CrgError) as e:
+        Regridder(grids.lonlat_grid(4, 2), grids.lonlat_grid(4, 2))
+    assert e.value.code == _lib.CRG_ERR_NO_DEVICE
+    tf = C.c_double()
+    assert _lib.lib().crg_fp64_peak(-1, C.byref(tf)) == _lib.CRG_ERR_NO_DEVICE
+
+
+def test_product_package_never_imports_oracle():
+    pkg = os.path.join(os.path.dirname(HEADER), "..", "conservativeregridding.jl_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
+                txt = open(os.path.join(root, f)).read()
+                assert "oracle" not in txt.lower().replace("no cpu fallback", ""), os.path.join(root, f)

