@@ -31,7 +31,7 @@ EXPORTS = [
     "crg_options_init", "crg_build", "crg_build_from_coo", "crg_free", "crg_dims", "crg_stats", "crg_areas",
     "crg_export_csc", "crg_export_csr", "crg_candidates", "crg_normalize", "crg_apply", "crg_apply_async",
     "crg_set_stream", "crg_synchronize", "crg_apply_bytes", "crg_last_error", "crg_device_count", "crg_version",
-    "crg_fp64_peak",
+    "crg_fp64_peak", "crg_launch_count",
 ]
 
 
@@ -44,7 +44,7 @@ class CrgError(RuntimeError):
 class Options(C.Structure):
     _fields_ = [("manifold", C.c_int32), ("normalize", C.c_int32), ("radius", C.c_double),
                 ("area_threshold", C.c_double), ("device", C.c_int32), ("build_transpose", C.c_int32),
-                ("keep_candidates", C.c_int32), ("reserved", C.c_int32)]
+                ("keep_candidates", C.c_int32), ("reserved", C.c_int32), ("stream", C.c_void_p)]
 
 
 class Cells(C.Structure):
@@ -127,6 +127,7 @@ def lib():
     L.crg_apply_bytes.argtypes = [vp, i32, i32, i64, P(i64)]
     L.crg_device_count.argtypes = [P(i32)]
     L.crg_fp64_peak.argtypes = [i32, P(f64)]
+    L.crg_launch_count.argtypes = [P(C.c_uint64)]
     for name in EXPORTS:
         if name not in ("crg_last_error", "crg_version"):
             getattr(L, name).restype = C.c_int
@@ -137,6 +138,12 @@ def lib():
 def check(rc: int):
     if rc != CRG_OK:
         raise CrgError(rc, lib().crg_last_error().decode(errors="replace"))
+
+
+def launch_count() -> int:
+    n = C.c_uint64(0)
+    check(lib().crg_launch_count(C.byref(n)))
+    return int(n.value)
 
 
 def device_count() -> int:

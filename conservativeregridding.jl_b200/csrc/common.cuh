@@ -35,7 +35,12 @@ inline int fail_cuda(cudaError_t e, const char *what, const char *file, int line
         if (_rc != CRG_OK) return _rc; \
     } while (0)
 
-#define CRG_LAUNCH_CHECK() CRG_CUDA(cudaGetLastError())
+extern unsigned long long g_launches;   // kernels launched by this library (crg_launch_count)
+#define CRG_LAUNCH_CHECK()                    \
+    do {                                      \
+        __atomic_add_fetch(&crg::g_launches, 1ull, __ATOMIC_RELAXED); \
+        CRG_CUDA(cudaGetLastError());         \
+    } while (0)
 
 // ---------------------------------------------------------------------------------------
 // stream-ordered device buffer (cudaMallocAsync pool: repeated builds reuse memory)

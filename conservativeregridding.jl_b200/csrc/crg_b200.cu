@@ -16,6 +16,7 @@
 
 namespace crg {
 thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 
 int set_error(int code, const char *fmt, ...) {
     va_list ap;
@@ -267,8 +268,10 @@ static int do_normalize(crg_regridder *R) {
     max_kernel<<<296, 256, 0, st>>>(R->A.vals.p, R->nnz, R->scratch_max.p);
     CRG_LAUNCH_CHECK();
     div_by_kernel<<<296, 256, 0, st>>>(R->A.vals.p, R->nnz, R->scratch_max.p);
-    if (R->has_At) div_by_kernel<<<296, 256, 0, st>>>(R->At.vals.p, R->nnz, R->scratch_max.p);
+    CRG_LAUNCH_CHECK();
+    if (R->has_At) { div_by_kernel<<<296, 256, 0, st>>>(R->At.vals.p, R->nnz, R->scratch_max.p); CRG_LAUNCH_CHECK(); }
     div_by_kernel<<<148, 256, 0, st>>>(R->dst_areas.p, R->n_dst, R->scratch_max.p);
+    CRG_LAUNCH_CHECK();
     div_by_kernel<<<148, 256, 0, st>>>(R->src_areas.p, R->n_src, R->scratch_max.p);
     CRG_LAUNCH_CHECK();
     return CRG_OK;
@@ -299,9 +302,8 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     DevBuf<unsigned int> nflip;
     CRG_TRY(nflip.alloc(2, st));
     CRG_CUDA(cudaMemsetAsync(nflip.p, 0, 2 * sizeof(unsigned int), st));
-    if (nd) cell_area_kernel<DIM><<<ceil_div(nd, 256), 256, 0, st>>>(gd.view, r2, R->dst_areas.p, gd.flip.p, nflip.p);
-    if (ns) cell_area_kernel<DIM><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, r2, R->src_areas.p, gs.flip.p, nflip.p + 1);
-    CRG_LAUNCH_CHECK();
+    if (nd) { cell_area_kernel<DIM><<<ceil_div(nd, 256), 256, 0, st>>>(gd.view, r2, R->dst_areas.p, gd.flip.p, nflip.p); CRG_LAUNCH_CHECK(); }
+    if (ns) { cell_area_kernel<DIM><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, r2, R->src_areas.p, gs.flip.p, nflip.p + 1); CRG_LAUNCH_CHECK(); }
     gd.view.flip = gd.flip.p;
     gs.view.flip = gs.flip.p;
     CRG_TRY(tm.mark());   // 1
@@ -316,9 +318,8 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     for (int k = 0; k < 2; ++k) { hst[k].lo[0] = hst[k].lo[1] = ~0ull; hst[k].hi[0] = hst[k].hi[1] = 0ull; }
     CRG_CUDA(cudaMemcpyAsync(dstats.p, hst, sizeof(hst), cudaMemcpyHostToDevice, st));
     const double big_chord = 2.0 * std::sin(BP_BIG_ANGLE / 2.0);
-    if (nd) bp_bounds_kernel<DIM><<<ceil_div(nd, 256), 256, 0, st>>>(gd.view, gd.diam.p, dstats.p, (float)big_chord);
-    if (ns) bp_bounds_kernel<DIM><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, gs.diam.p, dstats.p + 1, (float)big_chord);
-    CRG_LAUNCH_CHECK();
+    if (nd) { bp_bounds_kernel<DIM><<<ceil_div(nd, 256), 256, 0, st>>>(gd.view, gd.diam.p, dstats.p, (float)big_chord); CRG_LAUNCH_CHECK(); }
+    if (ns) { bp_bounds_kernel<DIM><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, gs.diam.p, dstats.p + 1, (float)big_chord); CRG_LAUNCH_CHECK(); }
     CRG_CUDA(cudaMemcpyAsync(hst, dstats.p, sizeof(hst), cudaMemcpyDeviceToHost, st));
     CRG_CUDA(cudaStreamSynchronize(st));
     CRG_TRY(tm.mark());   // 2
@@ -389,7 +390,7 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     CRG_CUDA(cudaMemsetAsync(counters.p, 0, sizeof(uint32_t) * 4, st));
     if (ns) bp_bin_kernel<DIM, false><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, gs.diam.p, P, bin_count.p, nullptr,
                                                                           nullptr, big_src.p, counters.p);
-    CRG_LAUNCH_CHECK();
+    if (ns) CRG_LAUNCH_CHECK();
     CRG_TRY((exclusive_scan<uint32_t, uint32_t>(bin_count.p, (int64_t)nbins, bin_start.p, st)));
     uint32_t h_entries = 0, h_counters[4] = {0, 0, 0, 0};
     CRG_CUDA(cudaMemcpyAsync(&h_entries, bin_start.p + nbins, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -403,7 +404,7 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     CRG_CUDA(cudaMemsetAsync(bin_count.p, 0, sizeof(uint32_t) * (nbins + 1), st));
     if (ns) bp_bin_kernel<DIM, true><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, gs.diam.p, P, bin_count.p, bin_start.p,
                                                                          entries.p, nullptr, nullptr);
-    CRG_LAUNCH_CHECK();
+    if (ns) CRG_LAUNCH_CHECK();
     CRG_TRY(tm.mark());   // 3
 
     // ---- K2b: destination queries (count / scan / fill) ---------------------------------------
@@ -414,7 +415,7 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     if (nd) bp_query_kernel<DIM, false><<<ceil_div(nd, 128), 128, 0, st>>>(
         gd.view, gd.diam.p, P, bin_start.p, entries.p, big_src.p, n_big_src, ns, cand_count.p, nullptr, nullptr,
         big_dst.p, counters.p + 1);
-    CRG_LAUNCH_CHECK();
+    if (nd) CRG_LAUNCH_CHECK();
     CRG_TRY((exclusive_scan<uint32_t, int64_t>(cand_count.p, nd, cand_off.p, st)));
     int64_t n_cand = 0;
     CRG_CUDA(cudaMemcpyAsync(&n_cand, cand_off.p + nd, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -430,7 +431,7 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     if (nd) bp_query_kernel<DIM, true><<<ceil_div(nd, 128), 128, 0, st>>>(
         gd.view, gd.diam.p, P, bin_start.p, entries.p, big_src.p, n_big_src, ns, nullptr, cand_off.p, pairs.p, nullptr,
         nullptr);
-    CRG_LAUNCH_CHECK();
+    if (nd) CRG_LAUNCH_CHECK();
     if (n_big_dst && ns) {
         dim3 grid((unsigned)std::min<int64_t>(ceil_div(ns, 256), 1024), (unsigned)n_big_dst);
         bp_fill_big_dst_kernel<<<grid, 256, 0, st>>>(big_dst.p, cand_off.p, ns, pairs.p);
@@ -501,6 +502,23 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     return CRG_OK;
 }
 
+// One library-owned stream per device, created on first use and shared by every handle that is
+// not given a caller stream: creating/destroying a stream per handle defeats the stream-ordered
+// allocator's block reuse (measured: ~30 ms per build on cfg5).
+static cudaStream_t g_dev_stream[64];
+static int device_stream(int dev, cudaStream_t *out) {
+    if (dev < 0 || dev >= 64) return set_error(CRG_ERR_INVALID, "device ordinal %d not supported", dev);
+    if (!g_dev_stream[dev]) {
+        cudaStream_t s;
+        CRG_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        cudaStream_t expected = nullptr;
+        if (!__atomic_compare_exchange_n(&g_dev_stream[dev], &expected, s, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE))
+            cudaStreamDestroy(s);
+    }
+    *out = g_dev_stream[dev];
+    return CRG_OK;
+}
+
 static int new_handle(const crg_options *opts, crg_regridder **out, DeviceGuard &guard) {
     CRG_TRY(check_device_available());
     int ndev = 0;
@@ -512,9 +530,10 @@ static int new_handle(const crg_options *opts, crg_regridder **out, DeviceGuard 
     R->opts = *opts;
     memset(&R->stats, 0, sizeof(R->stats));
     cudaError_t e = cudaGetDevice(&R->device);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&R->own_stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { delete R; return fail_cuda(e, "cudaStreamCreate", __FILE__, __LINE__); }
-    R->stream = R->own_stream;
+    if (e != cudaSuccess) { delete R; return fail_cuda(e, "cudaGetDevice", __FILE__, __LINE__); }
+    int rc = device_stream(R->device, &R->own_stream);
+    if (rc != CRG_OK) { delete R; return rc; }
+    R->stream = opts->stream ? (cudaStream_t)opts->stream : R->own_stream;
     // keep freed blocks in the pool: repeated builds/applies do not hit the driver allocator
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, R->device) == cudaSuccess) {
@@ -538,8 +557,7 @@ static void destroy_handle(crg_regridder *R) {
     rebind(R->At.rowptr); rebind(R->At.colidx); rebind(R->At.vals);
     rebind(R->dst_areas); rebind(R->src_areas); rebind(R->scratch_max); rebind(R->cand_pairs);
     rebind(R->stage_src); rebind(R->stage_dst);
-    if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
-    delete R;
+    delete R;   // buffers were released stream-ordered on the shared library stream; no sync needed
     if (prev >= 0) cudaSetDevice(prev);
     cudaGetLastError();
 }
@@ -649,6 +667,12 @@ extern "C" {
 const char *crg_last_error(void) { return g_err; }
 const char *crg_version(void) { return "crg_b200 0.1.0 (sm_100a)"; }
 
+int crg_launch_count(uint64_t *count) {
+    if (!count) return set_error(CRG_ERR_INVALID, "null count");
+    *count = __atomic_load_n(&g_launches, __ATOMIC_RELAXED);
+    return CRG_OK;
+}
+
 int crg_device_count(int32_t *count) {
     if (!count) return set_error(CRG_ERR_INVALID, "null count");
     int n = 0;
@@ -668,6 +692,7 @@ int crg_options_init(crg_options *o) {
     o->device = -1;
     o->build_transpose = 1;
     o->keep_candidates = 0;
+    o->stream = nullptr;
     return CRG_OK;
 }
 
@@ -867,6 +892,7 @@ int crg_fp64_peak(int32_t device, double *tflops) {
     for (int rep = 0; rep < 5; ++rep) {
         CRG_CUDA(cudaEventRecord(a));
         fp64_peak_kernel<<<blocks, threads>>>(out, iters);
+        __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED);
         CRG_CUDA(cudaEventRecord(b));
         CRG_CUDA(cudaEventSynchronize(b));
         float ms = 0.f;

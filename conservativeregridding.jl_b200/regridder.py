@@ -213,15 +213,33 @@ class B200Matrix:
 # Regridder
 # -----------------------------------------------------------------------------------------
 
+class _Lazy:
+    """A host vector materialised on first access and then shared (``is``) by R and transpose(R)."""
+
+    def __init__(self, make):
+        self._make = make
+        self._val = None
+
+    def get(self):
+        if self._val is None:
+            self._val = self._make()
+        return self._val
+
+
 class RegridderB200:
-    """``Regridder{W,A,V}`` (regridder.jl:25-36)."""
+    """``Regridder{W,A,V}`` (regridder.jl:25-36).  The area vectors are fetched from the device on
+    first access and the work vectors allocated on first use; transpose(R) shares the same objects."""
 
     def __init__(self, intersections: B200Matrix, dst_areas, src_areas, dst_temp, src_temp):
         self.intersections = intersections
-        self.dst_areas = dst_areas
-        self.src_areas = src_areas
-        self.dst_temp = dst_temp
-        self.src_temp = src_temp
+        wrap = lambda v: v if isinstance(v, _Lazy) else _Lazy(lambda v=v: v)  # noqa: E731
+        self._dst_areas, self._src_areas = wrap(dst_areas), wrap(src_areas)
+        self._dst_temp, self._src_temp = wrap(dst_temp), wrap(src_temp)
+
+    dst_areas = property(lambda self: self._dst_areas.get())
+    src_areas = property(lambda self: self._src_areas.get())
+    dst_temp = property(lambda self: self._dst_temp.get())
+    src_temp = property(lambda self: self._src_temp.get())
 
     @property
     def shape(self):
@@ -241,7 +259,7 @@ class RegridderB200:
 
 def transpose(R: RegridderB200) -> RegridderB200:
     """``LinearAlgebra.transpose(::Regridder)``: no copy, areas and temps swapped (regridder.jl:49-50)."""
-    return RegridderB200(R.intersections.T, R.src_areas, R.dst_areas, R.src_temp, R.dst_temp)
+    return RegridderB200(R.intersections.T, R._src_areas, R._dst_areas, R._src_temp, R._dst_temp)
 
 
 def _refresh_areas(R: RegridderB200):
@@ -258,7 +276,7 @@ def normalize_(R: RegridderB200) -> RegridderB200:
     return R
 
 
-def _make_options(manifold, normalize, radius, device, area_threshold, build_transpose, keep_candidates):
+def _make_options(manifold, normalize, radius, device, area_threshold, build_transpose, keep_candidates, stream=None):
     o = _lib.Options()
     _lib.check(_lib.lib().crg_options_init(C.byref(o)))
     o.manifold = manifold
@@ -268,22 +286,29 @@ def _make_options(manifold, normalize, radius, device, area_threshold, build_tra
     o.area_threshold = float(area_threshold)
     o.build_transpose = int(bool(build_transpose))
     o.keep_candidates = int(bool(keep_candidates))
+    o.stream = stream or None
     return o
 
 
 def _wrap(ptr, n_dst, n_src) -> RegridderB200:
     h = _Handle(ptr)
     M = B200Matrix(h, n_dst, n_src)
-    da = np.empty(n_dst)
-    sa = np.empty(n_src)
-    _lib.check(_lib.lib().crg_areas(ptr, da.ctypes.data, sa.ctypes.data))
-    return RegridderB200(M, da, sa, np.zeros(n_dst), np.zeros(n_src))
+
+    def fetch(which):
+        def make():
+            a = np.empty(n_dst if which == 0 else n_src)
+            _lib.check(_lib.lib().crg_areas(h.ptr, a.ctypes.data if which == 0 else None,
+                                            a.ctypes.data if which == 1 else None))
+            return a
+        return make
+    return RegridderB200(M, _Lazy(fetch(0)), _Lazy(fetch(1)), _Lazy(lambda: np.zeros(n_dst)),
+                         _Lazy(lambda: np.zeros(n_src)))
 
 
 def Regridder(dst, src, *, manifold: Optional[int] = None, normalize: bool = False,
               intersection_operator: Optional[Callable] = None, threaded=True, radius: Optional[float] = None,
               device: Optional[int] = None, area_threshold: float = 0.0, build_transpose: bool = True,
-              keep_candidates: bool = False, **_ignored) -> RegridderB200:
+              keep_candidates: bool = False, stream: Optional[int] = None, **_ignored) -> RegridderB200:
     """``Regridder(dst, src; normalize=false, intersection_operator, threaded, …)``
     (regridder.jl:105-163).  ``threaded`` is accepted and ignored (the device is the parallelism);
     a custom ``intersection_operator(src_polygon, dst_polygon) -> area`` is evaluated on the host for
@@ -302,7 +327,7 @@ def Regridder(dst, src, *, manifold: Optional[int] = None, normalize: bool = Fal
     L = _lib.lib()
     out = C.c_void_p()
     if intersection_operator is None:
-        o = _make_options(mf, normalize, radius, device, area_threshold, build_transpose, keep_candidates)
+        o = _make_options(mf, normalize, radius, device, area_threshold, build_transpose, keep_candidates, stream)
         _lib.check(L.crg_build(C.byref(o), C.byref(cd), C.byref(cs), C.byref(out)))
         return _wrap(out.value, gd.ncells, gs.ncells)
     # plugin path: device broad phase -> host operator per pair -> device assembly

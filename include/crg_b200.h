@@ -70,6 +70,8 @@ typedef struct crg_options {
                              /* transpose(R) and crg_export_csc; default 1                    */
     int32_t keep_candidates; /* keep the broad-phase pair list for crg_candidates (tests)     */
     int32_t reserved;
+    void *stream;            /* cudaStream_t to run on (e.g. the caller's current stream);     */
+                             /* NULL = a stream owned by the handle                           */
 } crg_options;
 
 /* A grid as the flat list of its cells in field-linear order (= collect(getcell(tree))).
@@ -153,6 +155,9 @@ int crg_synchronize(crg_regridder *r);
  * 12*nnz + 4*(n_out+1) + 8*n_out*[divide] + 8*K*(n_in + n_out).                             */
 int crg_apply_bytes(const crg_regridder *r, int32_t transpose, int32_t divide_by_area, int64_t K,
                     int64_t *bytes);
+
+/* Number of CUDA kernels this library has launched in the calling process so far. */
+int crg_launch_count(uint64_t *count);
 
 const char *crg_last_error(void);
 int crg_device_count(int32_t *count);

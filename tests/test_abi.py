@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     # sizes follow from the field lists in the header (natural alignment)
-    assert C.sizeof(_lib.Options) == 40
+    assert C.sizeof(_lib.Options) == 48
     assert C.sizeof(_lib.Cells) == 32
     o = _lib.Options()
     _lib.check(_lib.lib().crg_options_init(C.byref(o)))
