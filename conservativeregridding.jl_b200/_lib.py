@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(CSRC, "libcrgb200.so")
 SOURCES = ["crg_b200.cu"]
-HEADERS = ["common.cuh", "scan.cuh", "sort.cuh", "geom.cuh", "broadphase.cuh", "kernels.cuh"]
+HEADERS = ["common.cuh", "scan.cuh", "sort.cuh", "geom.cuh", "broadphase.cuh", "kernels.cuh", "sell.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -13,6 +13,7 @@
 #include "kernels.cuh"
 #include "scan.cuh"
 #include "sort.cuh"
+#include "sell.cuh"
 
 namespace crg {
 thread_local char g_err[512] = "";
@@ -46,6 +47,18 @@ struct Csr {
     int64_t n_rows = 0, n_cols = 0, nnz = 0;
     DevBuf<int32_t> rowptr, colidx;
     DevBuf<double> vals;
+    // SELL-32-sigma copy used by the SpMV (sell.cuh)
+    DevBuf<double> sell_vals, sell_partial;
+    DevBuf<int32_t> sell_cols, sell_perm, sell_rlen, sell_slice_off;
+    DevBuf<int4> sell_pieces;
+    DevBuf<unsigned int> sell_ticket;
+    DevBuf<uint32_t> sell_cut_base;
+    int sell_npieces = 0, sell_nslices = 0;
+    int64_t sell_padded = 0;
+    SellView sell_view() const {
+        return SellView{sell_vals.p, sell_cols.p, sell_perm.p, sell_rlen.p, sell_slice_off.p, sell_pieces.p,
+                        sell_cut_base.p, sell_partial.p, sell_ticket.p, sell_nslices, sell_npieces};
+    }
 };
 }  // namespace crg
 
@@ -174,6 +187,64 @@ struct Timer {
     }
 };
 
+static int alloc_csr(Csr &M, int64_t n_rows, int64_t n_cols, int64_t nnz, cudaStream_t st) {
+    M.n_rows = n_rows; M.n_cols = n_cols; M.nnz = nnz;
+    CRG_TRY(M.rowptr.alloc((size_t)n_rows + 1, st));
+    CRG_TRY(M.colidx.alloc((size_t)nnz, st));
+    CRG_TRY(M.vals.alloc((size_t)nnz, st));
+    CRG_CUDA(cudaMemsetAsync(M.rowptr.p, 0, sizeof(int32_t) * (size_t)(n_rows + 1), st));
+    return CRG_OK;
+}
+
+// CSR -> SELL-32-sigma (sell.cuh): window sort, slice offsets, piece list, scatter.
+static int build_sell(Csr &M, cudaStream_t st) {
+    M.sell_npieces = 0;
+    M.sell_padded = 0;
+    if (M.n_rows == 0) return CRG_OK;
+    const int nwin = (int)((M.n_rows + SELL_SIGMA - 1) / SELL_SIGMA);
+    const int64_t npos = (int64_t)nwin * SELL_SIGMA;
+    const int nslices = (int)(npos / 32);
+    DevBuf<int32_t> steps;
+    M.sell_nslices = nslices;
+    DevBuf<uint32_t> cnt, off;     // [0, nslices]: extra pieces, (nslices, 2 nslices]: partial slots
+    CRG_TRY(M.sell_perm.alloc((size_t)npos, st));
+    CRG_TRY(M.sell_rlen.alloc((size_t)npos, st));
+    CRG_TRY(M.sell_slice_off.alloc((size_t)nslices + 1, st));
+    CRG_TRY(steps.alloc((size_t)nslices, st));
+    CRG_TRY(cnt.alloc((size_t)2 * nslices, st));
+    CRG_TRY(off.alloc((size_t)2 * nslices + 2, st));
+    sell_sort_kernel<<<nwin, SELL_SIGMA, 0, st>>>(M.rowptr.p, M.n_rows, M.sell_perm.p, M.sell_rlen.p, steps.p);
+    CRG_LAUNCH_CHECK();
+    CRG_TRY((exclusive_scan<int32_t, int32_t>(steps.p, nslices, M.sell_slice_off.p, st)));
+    sell_count_kernel<<<ceil_div(nslices, 256), 256, 0, st>>>(steps.p, nslices, cnt.p, cnt.p + nslices);
+    CRG_LAUNCH_CHECK();
+    CRG_TRY((exclusive_scan<uint32_t, uint32_t>(cnt.p, nslices, off.p, st)));
+    CRG_TRY(M.sell_cut_base.alloc((size_t)nslices + 1, st));
+    CRG_TRY((exclusive_scan<uint32_t, uint32_t>(cnt.p + nslices, nslices, M.sell_cut_base.p, st)));
+    int32_t total_steps = 0;
+    uint32_t np = 0, nslots = 0;
+    CRG_CUDA(cudaMemcpyAsync(&total_steps, M.sell_slice_off.p + nslices, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CRG_CUDA(cudaMemcpyAsync(&np, off.p + nslices, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CRG_CUDA(cudaMemcpyAsync(&nslots, M.sell_cut_base.p + nslices, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CRG_CUDA(cudaStreamSynchronize(st));
+    M.sell_npieces = (int)np;
+    M.sell_padded = (int64_t)total_steps * 32;
+    CRG_TRY(M.sell_vals.alloc((size_t)M.sell_padded, st));
+    CRG_TRY(M.sell_cols.alloc((size_t)M.sell_padded, st));
+    CRG_TRY(M.sell_pieces.alloc((size_t)np, st));
+    CRG_TRY(M.sell_partial.alloc((size_t)nslots * 32, st));
+    CRG_TRY(M.sell_ticket.alloc((size_t)nslots, st));
+    CRG_CUDA(cudaMemsetAsync(M.sell_ticket.p, 0, sizeof(unsigned int) * (size_t)(nslots > 0 ? nslots : 1), st));
+    sell_pieces_kernel<<<ceil_div(nslices, 256), 256, 0, st>>>(steps.p, nslices, off.p, M.sell_cut_base.p, M.sell_pieces.p);
+    CRG_LAUNCH_CHECK();
+    sell_fill_kernel<<<ceil_div(npos, 256), 256, 0, st>>>(M.rowptr.p, M.colidx.p, M.vals.p, M.sell_perm.p, M.sell_slice_off.p,
+                                                          npos, M.sell_vals.p, M.sell_cols.p);
+    CRG_LAUNCH_CHECK();
+    return CRG_OK;
+}
+
+static int finish_csr(Csr &M, cudaStream_t st) { return build_sell(M, st); }
+
 // Sort COO (keys = row<<32|col, f64 values) -> CSR; optionally also the transposed CSR.
 // keys/vals buffers have capacity `cap` (>= n) and are consumed.
 static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &valA, int64_t n, bool row_sorted_hint,
@@ -221,27 +292,20 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
     R->nnz = nnz;
     // CSR(A)
     Csr &A = R->A;
-    A.n_rows = R->n_dst; A.n_cols = R->n_src; A.nnz = nnz;
-    CRG_TRY(A.rowptr.alloc((size_t)A.n_rows + 1, st));
-    CRG_TRY(A.colidx.alloc((size_t)nnz, st));
-    CRG_TRY(A.vals.alloc((size_t)nnz, st));
-    CRG_CUDA(cudaMemsetAsync(A.rowptr.p, 0, sizeof(int32_t) * (size_t)(A.n_rows + 1), st));
+    CRG_TRY(alloc_csr(A, R->n_dst, R->n_src, nnz, st));
     if (nnz > 0) {
         split_csr_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(ka, (const double *)va, nnz, A.n_rows, A.rowptr.p,
                                                                A.colidx.p, A.vals.p);
         CRG_LAUNCH_CHECK();
     }
+    CRG_TRY(finish_csr(A, st));
     *t_sort_csr1 = (int)tm.ev.size();
     CRG_TRY(tm.mark());
     // CSR(A^T): swap the key halves and (stably) sort by the new high word only
     R->has_At = false;
     if (R->opts.build_transpose) {
         Csr &T = R->At;
-        T.n_rows = R->n_src; T.n_cols = R->n_dst; T.nnz = nnz;
-        CRG_TRY(T.rowptr.alloc((size_t)T.n_rows + 1, st));
-        CRG_TRY(T.colidx.alloc((size_t)nnz, st));
-        CRG_TRY(T.vals.alloc((size_t)nnz, st));
-        CRG_CUDA(cudaMemsetAsync(T.rowptr.p, 0, sizeof(int32_t) * (size_t)(T.n_rows + 1), st));
+        CRG_TRY(alloc_csr(T, R->n_src, R->n_dst, nnz, st));
         int p3 = 0;
         if (nnz > 0) {
             swap_key_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(ka, nnz, ka);
@@ -252,6 +316,7 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
                                                                    T.colidx.p, T.vals.p);
             CRG_LAUNCH_CHECK();
         }
+        CRG_TRY(finish_csr(T, st));
         R->stats.sort_passes_csc = p3;
         R->has_At = true;
     }
@@ -270,6 +335,8 @@ static int do_normalize(crg_regridder *R) {
     div_by_kernel<<<296, 256, 0, st>>>(R->A.vals.p, R->nnz, R->scratch_max.p);
     CRG_LAUNCH_CHECK();
     if (R->has_At) { div_by_kernel<<<296, 256, 0, st>>>(R->At.vals.p, R->nnz, R->scratch_max.p); CRG_LAUNCH_CHECK(); }
+    for (Csr *M : {&R->A, &R->At})
+        if (M->sell_padded > 0) { div_by_kernel<<<296, 256, 0, st>>>(M->sell_vals.p, M->sell_padded, R->scratch_max.p); CRG_LAUNCH_CHECK(); }
     div_by_kernel<<<148, 256, 0, st>>>(R->dst_areas.p, R->n_dst, R->scratch_max.p);
     CRG_LAUNCH_CHECK();
     div_by_kernel<<<148, 256, 0, st>>>(R->src_areas.p, R->n_src, R->scratch_max.p);
@@ -555,6 +622,10 @@ static void destroy_handle(crg_regridder *R) {
     auto rebind = [&](auto &buf) { buf.s = st; buf.release(); };
     rebind(R->A.rowptr); rebind(R->A.colidx); rebind(R->A.vals);
     rebind(R->At.rowptr); rebind(R->At.colidx); rebind(R->At.vals);
+    for (Csr *M : {&R->A, &R->At}) {
+        rebind(M->sell_vals); rebind(M->sell_partial); rebind(M->sell_cols); rebind(M->sell_perm); rebind(M->sell_rlen);
+        rebind(M->sell_slice_off); rebind(M->sell_pieces); rebind(M->sell_ticket); rebind(M->sell_cut_base);
+    }
     rebind(R->dst_areas); rebind(R->src_areas); rebind(R->scratch_max); rebind(R->cand_pairs);
     rebind(R->stage_src); rebind(R->stage_dst);
     delete R;   // buffers were released stream-ordered on the shared library stream; no sync needed
@@ -599,9 +670,14 @@ static int apply_impl(crg_regridder *R, int transpose, int divide, double *dst, 
     }
     if (n_out > 0) {
         if (K == 1 && (level_fastest ? (ld_src == 1 && ld_dst == 1) : true)) {
-            const int nblk = ceil_div(n_out, 32 * (SPMV_THREADS / 32));
-            if (divide) spmv_kernel<true><<<nblk, SPMV_THREADS, 0, st>>>(M.rowptr.p, M.colidx.p, M.vals.p, xs, yd, areas, n_out);
-            else spmv_kernel<false><<<nblk, SPMV_THREADS, 0, st>>>(M.rowptr.p, M.colidx.p, M.vals.p, xs, yd, areas, n_out);
+            if (M.nnz == 0) {
+                CRG_CUDA(cudaMemsetAsync(yd, 0, sizeof(double) * (size_t)n_out, st));
+            } else {
+                const SellView V = M.sell_view();
+                const int nw = M.sell_nslices + M.sell_npieces;      // one warp per slice + extra pieces of cut slices
+                if (divide) spmv_sell_kernel<true><<<ceil_div(nw, 8), 256, 0, st>>>(V, xs, yd, areas);
+                else spmv_sell_kernel<false><<<ceil_div(nw, 8), 256, 0, st>>>(V, xs, yd, areas);
+            }
         } else if (level_fastest) {
             const int nblk = ceil_div(n_out, 8);
 #define CRG_LF(KT)                                                                                                   \

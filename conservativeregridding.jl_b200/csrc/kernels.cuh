@@ -1,5 +1,5 @@
 // kernels.cuh -- clip/area kernel, cell areas, COO -> CSR/CSC assembly helpers, normalize,
-// and the apply kernels (CSR SpMV / SpMM with the area division fused in).
+// and the CSR SpMM apply kernels (area division fused in).  The SpMV lives in sell.cuh.
 #pragma once
 #include "common.cuh"
 #include "geom.cuh"
@@ -132,61 +132,6 @@ __global__ void __launch_bounds__(256) div_by_kernel(double *__restrict__ v, int
     const double d = *m;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         v[i] = v[i] / d;
-}
-
-// =======================================================================================
-// K7: CSR SpMV, y = A x (./ areas).  One warp per 32 consecutive rows: the warp streams the
-// rows' contiguous nnz range in coalesced 256-element chunks (val * x[col] staged in shared
-// memory), and each lane sums the part of the chunk that belongs to its own row, in column
-// order.  A chunk lying entirely inside one (long) row is reduced cooperatively instead.
-// Replaces mul! + the separate `dst ./= dst_areas` pass (regrid.jl:95-118).  HBM-bound:
-// 12 B/nnz + 4 B/row pointer + 8 B/row area + 8 B/row output + the x gather.
-// =======================================================================================
-constexpr int SPMV_THREADS = 256;
-constexpr int SPMV_CHUNK = 256;
-__device__ __forceinline__ int spmv_skew(int i) { return i + (i >> 3); }
-
-template <bool DIVIDE>
-__global__ void __launch_bounds__(SPMV_THREADS) spmv_kernel(const int32_t *__restrict__ rowptr,
-                                                            const int32_t *__restrict__ colidx,
-                                                            const double *__restrict__ vals,
-                                                            const double *__restrict__ x, double *__restrict__ y,
-                                                            const double *__restrict__ areas, int64_t n_rows) {
-    __shared__ double sbuf[SPMV_THREADS / 32][SPMV_CHUNK + SPMV_CHUNK / 8];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int64_t r0 = ((int64_t)blockIdx.x * (SPMV_THREADS / 32) + wid) * 32;
-    if (r0 >= n_rows) return;
-    const int64_t r = r0 + lane;
-    const int a = rowptr[r < n_rows ? r : n_rows];
-    const int b = rowptr[r + 1 < n_rows ? r + 1 : n_rows];
-    const int start = __shfl_sync(CRG_FULL, a, 0), end = __shfl_sync(CRG_FULL, b, 31);
-    double *sb = sbuf[wid];
-    double acc = 0.0;
-    for (int c0 = start; c0 < end; c0 += SPMV_CHUNK) {
-        const int cend = min(c0 + SPMV_CHUNK, end);
-        double p[SPMV_CHUNK / 32];
-#pragma unroll
-        for (int u = 0; u < SPMV_CHUNK / 32; ++u) {
-            const int idx = c0 + u * 32 + lane;
-            p[u] = idx < end ? vals[idx] * __ldg(&x[colidx[idx]]) : 0.0;
-        }
-        const unsigned owner = __ballot_sync(CRG_FULL, a <= c0 && b >= cend && b > a);
-        if (owner) {   // whole chunk inside one row: cooperative reduction
-            double s = 0.0;
-#pragma unroll
-            for (int u = 0; u < SPMV_CHUNK / 32; ++u) s += p[u];
-            s = warp_sum(s);
-            if (lane == __ffs(owner) - 1) acc += s;
-            continue;
-        }
-#pragma unroll
-        for (int u = 0; u < SPMV_CHUNK / 32; ++u) sb[spmv_skew(u * 32 + lane)] = p[u];
-        __syncwarp();
-        const int lo = max(a, c0) - c0, hi = min(b, cend) - c0;
-        for (int k = lo; k < hi; ++k) acc += sb[spmv_skew(k)];
-        __syncwarp();
-    }
-    if (r < n_rows) y[r] = DIVIDE ? acc / areas[r] : acc;
 }
 
 // =======================================================================================

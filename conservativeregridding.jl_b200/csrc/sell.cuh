@@ -1,0 +1,184 @@
+// sell.cuh -- K7: SpMV y = (A x) ./ areas on a SELL-32-sigma copy of the matrix.
+//
+// Replaces LinearAlgebra.mul! + the separate `dst ./= dst_areas` pass
+// (/root/reference/src/regridder/regrid.jl:95-118).  HBM-bound: 12 B/nnz of matrix data dominate.
+//
+// Regridding matrices have short rows (3..15 entries) of locally similar length, which is the
+// worst case for CSR on a GPU (every load either uncoalesced or behind a dependent row-pointer
+// chain).  At assembly the rows are therefore re-laid out once in sliced ELLPACK:
+//   * rows are sorted by length inside windows of SELL_SIGMA rows (stable, so equally long
+//     neighbours stay neighbours) -> perm[], rlen[];
+//   * 32 consecutive sorted rows form a slice, padded to its longest row; entry j of lane l is
+//     stored at (slice_off + j) * 32 + l, so one warp instruction reads 32 consecutive values
+//     (256 B) / column indices (128 B) -- perfectly coalesced, no shared memory, no barriers;
+//   * slices taller than SELL_HP steps (polar rows) are cut into pieces of SELL_HP steps.
+// The kernel runs one warp per piece, one lane per row: all loads of a step are independent of
+// the previous step, lanes gather x for neighbouring rows at the same position (neighbouring
+// source cells -> few 128 B lines per gather instruction).  Pieces of a cut slice leave their
+// partial sums in scratch; the last piece to arrive (ticket) adds them in piece order, so the
+// result is deterministic.  Padding measured on BASELINE cfg2: 0.8 % (forward), 1.9 % (transpose).
+#pragma once
+#include "common.cuh"
+
+namespace crg {
+
+constexpr int SELL_SIGMA = 1024;   // sorting window (rows)
+constexpr int SELL_HP = 32;        // max steps per piece
+constexpr int SELL_UNR = 4;
+
+struct SellView {
+    const double *vals;        // padded, slice-major
+    const int32_t *cols;
+    const int32_t *perm;       // sorted position -> original row, -1 for padding rows
+    const int32_t *rlen;       // sorted position -> row length
+    const int32_t *slice_off;  // [nslices + 1], in steps
+    const int4 *pieces;        // extra pieces (q >= 1) of cut slices: {slice, step_begin, partial_base, q | npieces << 16}
+    const uint32_t *cut_base;  // [nslices] partial-slot base of a cut slice (read only when steps > SELL_HP)
+    double *partial;           // [n_partial_slots][32]
+    unsigned int *ticket;      // [n_partial_slots]
+    int nslices;
+    int npieces;               // number of extra pieces
+};
+
+// ---- build step 1: sort the rows of each window by decreasing length ----------------------------------
+__global__ void __launch_bounds__(SELL_SIGMA) sell_sort_kernel(const int32_t *__restrict__ rowptr, int64_t n_rows,
+                                                               int32_t *__restrict__ perm, int32_t *__restrict__ rlen,
+                                                               int32_t *__restrict__ slice_steps) {
+    __shared__ uint64_t key[SELL_SIGMA];
+    const int t = threadIdx.x;
+    const int64_t r = (int64_t)blockIdx.x * SELL_SIGMA + t;
+    uint32_t len = 0;
+    if (r < n_rows) len = (uint32_t)(rowptr[r + 1] - rowptr[r]);
+    // descending by length, ascending by original position (stable); padding rows (len 0, beyond
+    // n_rows) sort last because their position is largest
+    key[t] = ((uint64_t)len << 32) | (uint32_t)(SELL_SIGMA - 1 - t);
+    __syncthreads();
+    for (int k = 2; k <= SELL_SIGMA; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int ixj = t ^ j;
+            if (ixj > t) {
+                const uint64_t a = key[t], b = key[ixj];
+                const bool desc = (t & k) == 0;       // final order: descending
+                if (desc ? (a < b) : (a > b)) { key[t] = b; key[ixj] = a; }
+            }
+            __syncthreads();
+        }
+    const uint64_t kk = key[t];
+    const int src = SELL_SIGMA - 1 - (int)(uint32_t)kk;
+    const int64_t rr = (int64_t)blockIdx.x * SELL_SIGMA + src;
+    const int64_t pos = (int64_t)blockIdx.x * SELL_SIGMA + t;
+    perm[pos] = rr < n_rows ? (int32_t)rr : -1;
+    rlen[pos] = (int32_t)(kk >> 32);
+    if ((t & 31) == 0) slice_steps[pos >> 5] = (int32_t)(kk >> 32);   // first lane of a slice is its longest row
+}
+
+// ---- build step 2: pieces per slice (after exclusive scans of piece / partial-slot counts) --------------
+__global__ void __launch_bounds__(256) sell_count_kernel(const int32_t *__restrict__ slice_steps, int nslices,
+                                                         uint32_t *__restrict__ npieces, uint32_t *__restrict__ nslots) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslices) return;
+    const int steps = slice_steps[s];
+    const int np = steps <= SELL_HP ? 1 : (steps + SELL_HP - 1) / SELL_HP;
+    npieces[s] = np - 1;                 // piece 0 is implicit (one warp per slice)
+    nslots[s] = np > 1 ? np : 0;
+}
+__global__ void __launch_bounds__(256) sell_pieces_kernel(const int32_t *__restrict__ slice_steps, int nslices,
+                                                          const uint32_t *__restrict__ piece_off,
+                                                          const uint32_t *__restrict__ slot_off, int4 *__restrict__ pieces) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslices) return;
+    const int steps = slice_steps[s];
+    const int np = steps <= SELL_HP ? 1 : (steps + SELL_HP - 1) / SELL_HP;
+    for (int q = 1; q < np; ++q)
+        pieces[piece_off[s] + q - 1] = make_int4(s, q * SELL_HP, (int)slot_off[s], q | (np << 16));
+}
+
+// ---- build step 3: scatter the CSR entries into the slices ----------------------------------------------
+__global__ void __launch_bounds__(256) sell_fill_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                                                        const double *__restrict__ vals, const int32_t *__restrict__ perm,
+                                                        const int32_t *__restrict__ slice_off, int64_t npos,
+                                                        double *__restrict__ svals, int32_t *__restrict__ scols) {
+    const int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= npos) return;
+    const int lane = (int)(pos & 31);
+    const int64_t s = pos >> 5;
+    const int off = slice_off[s], steps = slice_off[s + 1] - off;
+    const int r = perm[pos];
+    int a = 0, len = 0;
+    if (r >= 0) { a = rowptr[r]; len = rowptr[r + 1] - a; }
+    for (int j = 0; j < steps; ++j) {
+        const size_t dst = ((size_t)off + j) * 32 + lane;
+        const bool ok = j < len;
+        svals[dst] = ok ? vals[a + j] : 0.0;
+        scols[dst] = ok ? colidx[a + j] : 0;
+    }
+}
+
+// ---- the SpMV ----------------------------------------------------------------------------------------------
+// Pieces of a cut slice leave their partial sums in scratch; the last one to arrive adds them in order.
+template <bool DIVIDE>
+__device__ __forceinline__ void sell_finish_cut(const SellView &S, int base, int q, int np, int lane, int r, double acc,
+                                                double area, double *__restrict__ y) {
+    S.partial[((size_t)base + q) * 32 + lane] = acc;
+    __syncwarp();
+    unsigned prev = 0;
+    if (lane == 0) asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(S.ticket + base) : "memory");
+    prev = __shfl_sync(CRG_FULL, prev, 0);
+    if (prev != (unsigned)(np - 1)) return;
+    double sum = 0.0;
+    for (int t = 0; t < np; ++t) sum += __ldcg(&S.partial[((size_t)base + t) * 32 + lane]);
+    if (r >= 0) y[r] = DIVIDE ? sum / area : sum;
+    if (lane == 0) S.ticket[base] = 0;                  // ready for the next launch
+}
+
+// One warp per slice (lane = row), SELL_UNR steps in flight at once.  Warps beyond the slice range run
+// the extra pieces of cut slices.
+template <bool DIVIDE>
+__global__ void __launch_bounds__(256) spmv_sell_kernel(SellView S, const double *__restrict__ x, double *__restrict__ y,
+                                                        const double *__restrict__ areas) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int s, j0 = 0, base = -1, q = 0;
+    if (w < S.nslices) {
+        s = w;
+    } else {                                          // extra piece of a cut slice (rare)
+        if (w - S.nslices >= S.npieces) return;
+        const int4 d = __ldg(&S.pieces[w - S.nslices]);
+        s = d.x; j0 = d.y; base = d.z; q = d.w & 0xffff;
+    }
+    const int off = __ldg(&S.slice_off[s]);
+    const int steps = __ldg(&S.slice_off[s + 1]) - off;
+    const int64_t pos = (int64_t)s * 32 + lane;
+    const int len = __ldg(&S.rlen[pos]);
+    const int r = __ldg(&S.perm[pos]);
+    const int jend = min(len, j0 + SELL_HP);            // this lane's last step (exclusive) in this piece
+    const int wend = min(steps, j0 + SELL_HP);          // the slice's (lane 0 holds its longest row)
+    double area = 1.0;
+    if (DIVIDE && r >= 0) area = __ldg(&areas[r]);
+    const double *vp = S.vals + ((size_t)off + j0) * 32 + lane;
+    const int32_t *cp = S.cols + ((size_t)off + j0) * 32 + lane;
+    double acc = 0.0;
+    for (int j = j0; j < wend; j += SELL_UNR) {
+        int c[SELL_UNR];
+        double v[SELL_UNR], xv[SELL_UNR];
+#pragma unroll
+        for (int u = 0; u < SELL_UNR; ++u) {
+            const bool ok = j + u < jend;
+            c[u] = ok ? __ldg(cp + (size_t)u * 32) : 0;
+            v[u] = ok ? __ldg(vp + (size_t)u * 32) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < SELL_UNR; ++u) xv[u] = (j + u < jend) ? __ldg(&x[c[u]]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < SELL_UNR; ++u) if (j + u < jend) acc += v[u] * xv[u];
+        vp += SELL_UNR * 32; cp += SELL_UNR * 32;
+    }
+    if (steps <= SELL_HP) {                             // the whole slice is this piece
+        if (r >= 0) y[r] = DIVIDE ? acc / area : acc;
+        return;
+    }
+    if (base < 0) base = (int)__ldg(&S.cut_base[s]);    // piece 0 of a cut slice
+    sell_finish_cut<DIVIDE>(S, base, q, (steps + SELL_HP - 1) / SELL_HP, lane, r, acc, area, y);
+}
+
+}  // namespace crg

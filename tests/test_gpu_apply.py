@@ -124,3 +124,46 @@ def test_long_rows_and_empty_rows(gpu):
     assert (y[np.diff(A.indptr) == 0] == 0).all()
     xb = np.zeros(src.ncells); regrid_(xb, transpose(R), np.ones(dst.ncells))
     assert np.allclose(xb, 1.0, atol=1e-9)
+
+
+@pytest.mark.parametrize("case", ["short", "long", "mixed", "empty_runs", "exact_chunks", "one_row"])
+def test_spmv_stream_kernel_stress(gpu, case):
+    """K7 (TMA-streamed nnz chunks of 2048): rows spanning several chunks, long segments, runs of
+    empty rows, nnz an exact multiple of the chunk, single dense row -- vs scipy on the same matrix."""
+    import scipy.sparse as sp
+    from crg_b200.regridder import regridder_from_coo
+    rng = np.random.default_rng(hash(case) % 2 ** 31)
+    n_src = 5000
+    if case == "short":
+        lens = rng.integers(1, 6, 20000)
+    elif case == "long":
+        lens = rng.integers(1500, 7000, 12)
+    elif case == "mixed":
+        lens = np.where(rng.random(6000) < 0.01, rng.integers(100, 5000, 6000), rng.integers(0, 12, 6000))
+    elif case == "empty_runs":
+        lens = np.zeros(30000, dtype=np.int64); lens[rng.choice(30000, 300, replace=False)] = rng.integers(1, 400, 300)
+        lens[-5000:] = 0; lens[:4000] = 0
+    elif case == "exact_chunks":
+        lens = np.full(1024, 8)                  # 8192 nnz = 4 chunks exactly, rows aligned to chunk borders
+    else:
+        lens = np.array([4999])
+    lens = np.minimum(lens, n_src)
+    n_dst = len(lens)
+    rows = np.repeat(np.arange(n_dst), lens)
+    cols = np.concatenate([rng.choice(n_src, l, replace=False) for l in lens]) if rows.size else np.zeros(0, np.int64)
+    vals = rng.random(rows.size) + 0.5
+    da, sa = rng.random(n_dst) + 0.5, rng.random(n_src) + 0.5
+    R = regridder_from_coo(n_dst, n_src, rows, cols, vals, da, sa)
+    A = sp.coo_matrix((vals, (rows, cols)), shape=(n_dst, n_src)).tocsr()
+    x = rng.random(n_src)
+    y = np.full(n_dst, np.nan); regrid_(y, R, x)
+    assert np.allclose(y, (A @ x) / da, rtol=1e-12, atol=1e-14)
+    y2 = np.full(n_dst, np.nan); regrid_(y2, R, x, normalize=False)
+    assert np.allclose(y2, A @ x, rtol=1e-12, atol=1e-14)
+    yt = rng.random(n_dst)
+    xb = np.full(n_src, np.nan); regrid_(xb, transpose(R), yt)
+    assert np.allclose(xb, (A.T @ yt) / sa, rtol=1e-12, atol=1e-14)
+    # repeated launches reuse the self-resetting completion ticket
+    for _ in range(3):
+        y3 = np.zeros(n_dst); regrid_(y3, R, x)
+        assert np.array_equal(y3, y)
