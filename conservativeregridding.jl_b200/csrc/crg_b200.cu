@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdlib>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -18,6 +19,7 @@
 namespace crg {
 thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;
+thread_local Arena *t_arena = nullptr;
 
 int set_error(int code, const char *fmt, ...) {
     va_list ap;
@@ -135,7 +137,7 @@ static int stage_cells(const crg_cells *c, int dim, cudaStream_t st, DevCells *o
             CRG_CUDA(cudaStreamSynchronize(st));
         } else {
             last = c->offsets[n];
-            CRG_TRY(out->off_own.alloc((size_t)n + 1, st));
+            CRG_TRY(out->off_own.alloc_tmp((size_t)n + 1, st));
             CRG_CUDA(cudaMemcpyAsync(out->off_own.p, c->offsets, sizeof(int32_t) * (size_t)(n + 1),
                                      cudaMemcpyHostToDevice, st));
             doff = out->off_own.p;
@@ -144,7 +146,7 @@ static int stage_cells(const crg_cells *c, int dim, cudaStream_t st, DevCells *o
         out->total_verts = last;
         if (n > 0) {
             DevBuf<int> bad;
-            CRG_TRY(bad.alloc(1, st));
+            CRG_TRY(bad.alloc_tmp(1, st));
             CRG_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
             check_offsets_kernel<<<ceil_div(n, 256), 256, 0, st>>>(doff, n, CRG_MAX_VERTS, bad.p);
             CRG_LAUNCH_CHECK();
@@ -160,7 +162,7 @@ static int stage_cells(const crg_cells *c, int dim, cudaStream_t st, DevCells *o
     if (is_device_ptr(c->verts)) {
         out->view.verts = c->verts;
     } else {
-        CRG_TRY(out->verts_own.alloc((size_t)out->total_verts * dim, st));
+        CRG_TRY(out->verts_own.alloc_tmp((size_t)out->total_verts * dim, st));
         CRG_CUDA(cudaMemcpyAsync(out->verts_own.p, c->verts, sizeof(double) * (size_t)out->total_verts * dim,
                                  cudaMemcpyHostToDevice, st));
         out->view.verts = out->verts_own.p;
@@ -210,9 +212,9 @@ static int build_sell(Csr &M, cudaStream_t st) {
     CRG_TRY(M.sell_perm.alloc((size_t)npos, st));
     CRG_TRY(M.sell_rlen.alloc((size_t)npos, st));
     CRG_TRY(M.sell_slice_off.alloc((size_t)nslices + 1, st));
-    CRG_TRY(steps.alloc((size_t)nslices, st));
-    CRG_TRY(cnt.alloc((size_t)2 * nslices, st));
-    CRG_TRY(off.alloc((size_t)2 * nslices + 2, st));
+    CRG_TRY(steps.alloc_tmp((size_t)nslices, st));
+    CRG_TRY(cnt.alloc_tmp((size_t)2 * nslices, st));
+    CRG_TRY(off.alloc_tmp((size_t)2 * nslices + 2, st));
     sell_sort_kernel<<<nwin, SELL_SIGMA, 0, st>>>(M.rowptr.p, M.n_rows, M.sell_perm.p, M.sell_rlen.p, steps.p);
     CRG_LAUNCH_CHECK();
     CRG_TRY((exclusive_scan<int32_t, int32_t>(steps.p, nslices, M.sell_slice_off.p, st)));
@@ -247,34 +249,80 @@ static int finish_csr(Csr &M, cudaStream_t st) { return build_sell(M, st); }
 
 // Sort COO (keys = row<<32|col, f64 values) -> CSR; optionally also the transposed CSR.
 // keys/vals buffers have capacity `cap` (>= n) and are consumed.
-static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &valA, int64_t n, bool row_sorted_hint,
+// COO (keys = row<<32|col, f64 values) -> CSR(A) and, optionally, CSR(A^T).
+// keys/vals have at least n elements and are consumed.
+//   row_sorted_unique = true  (build path: the stable compaction of K3 leaves the triples grouped by
+//     increasing row, every pair once): one stable pass over the column bits gives the (col, row)
+//     order = CSC; a further stable pass over the row bits gives (row, col) = CSR.
+//   row_sorted_unique = false (crg_build_from_coo: arbitrary order, duplicates): full-key sort,
+//     segmented duplicate sum, then the column-bit passes for the transpose.
+static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &valA, int64_t n, bool row_sorted_unique,
                     Timer &tm, int *t_sort_csr0, int *t_sort_csr1, int *t_sort_csc1) {
     cudaStream_t st = R->stream;
     const int bits_src = ilog2_ceil((uint64_t)(R->n_src > 1 ? R->n_src : 2));
     const int bits_dst = ilog2_ceil((uint64_t)(R->n_dst > 1 ? R->n_dst : 2));
-    (void)row_sorted_hint;
     DevBuf<uint64_t> keyB;
     DevBuf<double> valB;
-    CRG_TRY(keyB.alloc((size_t)(n > 0 ? n : 1), st));
-    CRG_TRY(valB.alloc((size_t)(n > 0 ? n : 1), st));
+    CRG_TRY(keyB.alloc_tmp((size_t)(n > 0 ? n : 1), st));
+    CRG_TRY(valB.alloc_tmp((size_t)(n > 0 ? n : 1), st));
     *t_sort_csr0 = (int)tm.ev.size();
     CRG_TRY(tm.mark());
     uint64_t *ka = keyA.p, *kb = keyB.p;
     uint64_t *va = (uint64_t *)valA.p, *vb = (uint64_t *)valB.p;
     bool inb = false;
-    int p1 = 0, p2 = 0;
-    // LSD: low word (src) digits first, then the high word (dst) digits
+    int p1 = 0, p2 = 0, p3 = 0;
+    int64_t nnz = n;
+    Csr &A = R->A;
+    Csr &T = R->At;
+    R->has_At = false;
+    if (n >= ((int64_t)1 << 31)) return set_error(CRG_ERR_NOMEM, "nnz=%lld exceeds int32 indexing", (long long)n);
+
+    if (row_sorted_unique) {
+        R->nnz = nnz;
+        // (col, row) order
+        CRG_TRY(radix_sort_pairs(ka, va, kb, vb, n, 0, bits_src, &inb, &p1, st));
+        if (inb) { std::swap(ka, kb); std::swap(va, vb); }
+        if (R->opts.build_transpose) {
+            CRG_TRY(alloc_csr(T, R->n_src, R->n_dst, nnz, st));
+            if (nnz > 0) {
+                swap_key_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(ka, nnz, kb);      // kb = col<<32 | row
+                CRG_LAUNCH_CHECK();
+                split_csr_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(kb, (const double *)va, nnz, T.n_rows, T.rowptr.p,
+                                                                       T.colidx.p, T.vals.p);
+                CRG_LAUNCH_CHECK();
+            }
+            CRG_TRY(finish_csr(T, st));
+            R->has_At = true;
+        }
+        R->stats.sort_passes_csc = p1;
+        *t_sort_csr1 = (int)tm.ev.size();     // (phase names: "sort_csr" = column passes + CSC, "sort_csc" = row passes + CSR)
+        CRG_TRY(tm.mark());
+        // (row, col) order
+        CRG_TRY(radix_sort_pairs(ka, va, kb, vb, n, 32, 32 + bits_dst, &inb, &p2, st));
+        if (inb) { std::swap(ka, kb); std::swap(va, vb); }
+        R->stats.sort_passes_csr = p2;
+        CRG_TRY(alloc_csr(A, R->n_dst, R->n_src, nnz, st));
+        if (nnz > 0) {
+            split_csr_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(ka, (const double *)va, nnz, A.n_rows, A.rowptr.p,
+                                                                   A.colidx.p, A.vals.p);
+            CRG_LAUNCH_CHECK();
+        }
+        CRG_TRY(finish_csr(A, st));
+        *t_sort_csc1 = (int)tm.ev.size();
+        CRG_TRY(tm.mark());
+        return CRG_OK;
+    }
+
+    // ---- general path -------------------------------------------------------------------------------
     CRG_TRY(radix_sort_pairs(ka, va, kb, vb, n, 0, bits_src, &inb, &p1, st));
     if (inb) { std::swap(ka, kb); std::swap(va, vb); }
     CRG_TRY(radix_sort_pairs(ka, va, kb, vb, n, 32, 32 + bits_dst, &inb, &p2, st));
     if (inb) { std::swap(ka, kb); std::swap(va, vb); }
     R->stats.sort_passes_csr = p1 + p2;
-    // duplicate summation (segmented reduce over equal keys)
-    int64_t nnz = n;
-    if (n > 0) {
+    if (n > 0) {   // duplicate summation (segmented reduce over equal keys)
         DevBuf<uint32_t> flags, pos;
-        CRG_TRY(flags.alloc((size_t)n, st));
-        CRG_TRY(pos.alloc((size_t)n + 1, st));
+        CRG_TRY(flags.alloc_tmp((size_t)n, st));
+        CRG_TRY(pos.alloc_tmp((size_t)n + 1, st));
         mark_heads_kernel<<<ceil_div(n, 256), 256, 0, st>>>(ka, n, flags.p);
         CRG_LAUNCH_CHECK();
         CRG_TRY((exclusive_scan<uint32_t, uint32_t>(flags.p, n, pos.p, st)));
@@ -288,10 +336,7 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
             nnz = nu;
         }
     }
-    if (nnz >= ((int64_t)1 << 31)) return set_error(CRG_ERR_NOMEM, "nnz=%lld exceeds int32 indexing", (long long)nnz);
     R->nnz = nnz;
-    // CSR(A)
-    Csr &A = R->A;
     CRG_TRY(alloc_csr(A, R->n_dst, R->n_src, nnz, st));
     if (nnz > 0) {
         split_csr_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(ka, (const double *)va, nnz, A.n_rows, A.rowptr.p,
@@ -301,12 +346,8 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
     CRG_TRY(finish_csr(A, st));
     *t_sort_csr1 = (int)tm.ev.size();
     CRG_TRY(tm.mark());
-    // CSR(A^T): swap the key halves and (stably) sort by the new high word only
-    R->has_At = false;
-    if (R->opts.build_transpose) {
-        Csr &T = R->At;
+    if (R->opts.build_transpose) {   // swap the key halves and (stably) sort by the new high word only
         CRG_TRY(alloc_csr(T, R->n_src, R->n_dst, nnz, st));
-        int p3 = 0;
         if (nnz > 0) {
             swap_key_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(ka, nnz, ka);
             CRG_LAUNCH_CHECK();
@@ -364,10 +405,10 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     // ---- K4: areas + orientation ----------------------------------------------------------
     CRG_TRY(R->dst_areas.alloc((size_t)nd, st));
     CRG_TRY(R->src_areas.alloc((size_t)ns, st));
-    CRG_TRY(gd.flip.alloc((size_t)nd, st));
-    CRG_TRY(gs.flip.alloc((size_t)ns, st));
+    CRG_TRY(gd.flip.alloc_tmp((size_t)nd, st));
+    CRG_TRY(gs.flip.alloc_tmp((size_t)ns, st));
     DevBuf<unsigned int> nflip;
-    CRG_TRY(nflip.alloc(2, st));
+    CRG_TRY(nflip.alloc_tmp(2, st));
     CRG_CUDA(cudaMemsetAsync(nflip.p, 0, 2 * sizeof(unsigned int), st));
     if (nd) { cell_area_kernel<DIM><<<ceil_div(nd, 256), 256, 0, st>>>(gd.view, r2, R->dst_areas.p, gd.flip.p, nflip.p); CRG_LAUNCH_CHECK(); }
     if (ns) { cell_area_kernel<DIM><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, r2, R->src_areas.p, gs.flip.p, nflip.p + 1); CRG_LAUNCH_CHECK(); }
@@ -376,10 +417,10 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     CRG_TRY(tm.mark());   // 1
 
     // ---- K1: bounds -------------------------------------------------------------------------
-    CRG_TRY(gd.diam.alloc((size_t)nd, st));
-    CRG_TRY(gs.diam.alloc((size_t)ns, st));
+    CRG_TRY(gd.diam.alloc_tmp((size_t)nd, st));
+    CRG_TRY(gs.diam.alloc_tmp((size_t)ns, st));
     DevBuf<BPStats> dstats;
-    CRG_TRY(dstats.alloc(2, st));
+    CRG_TRY(dstats.alloc_tmp(2, st));
     BPStats hst[2];
     memset(hst, 0, sizeof(hst));
     for (int k = 0; k < 2; ++k) { hst[k].lo[0] = hst[k].lo[1] = ~0ull; hst[k].hi[0] = hst[k].hi[1] = 0ull; }
@@ -448,11 +489,11 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     // ---- K2a: bin the source cells (count / scan / fill) ------------------------------------
     DevBuf<uint32_t> bin_count, bin_start, counters;
     DevBuf<int32_t> big_src, big_dst;
-    CRG_TRY(bin_count.alloc(nbins + 1, st));
-    CRG_TRY(bin_start.alloc(nbins + 1, st));
-    CRG_TRY(counters.alloc(4, st));
-    CRG_TRY(big_src.alloc((size_t)ns, st));
-    CRG_TRY(big_dst.alloc((size_t)nd, st));
+    CRG_TRY(bin_count.alloc_tmp(nbins + 1, st));
+    CRG_TRY(bin_start.alloc_tmp(nbins + 1, st));
+    CRG_TRY(counters.alloc_tmp(4, st));
+    CRG_TRY(big_src.alloc_tmp((size_t)ns, st));
+    CRG_TRY(big_dst.alloc_tmp((size_t)nd, st));
     CRG_CUDA(cudaMemsetAsync(bin_count.p, 0, sizeof(uint32_t) * (nbins + 1), st));
     CRG_CUDA(cudaMemsetAsync(counters.p, 0, sizeof(uint32_t) * 4, st));
     if (ns) bp_bin_kernel<DIM, false><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, gs.diam.p, P, bin_count.p, nullptr,
@@ -467,7 +508,7 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     S.n_bin_entries = h_entries;
     S.n_big_src = n_big_src;
     DevBuf<int4> entries;
-    CRG_TRY(entries.alloc((size_t)h_entries, st));
+    CRG_TRY(entries.alloc_tmp((size_t)h_entries, st));
     CRG_CUDA(cudaMemsetAsync(bin_count.p, 0, sizeof(uint32_t) * (nbins + 1), st));
     if (ns) bp_bin_kernel<DIM, true><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, gs.diam.p, P, bin_count.p, bin_start.p,
                                                                          entries.p, nullptr, nullptr);
@@ -477,8 +518,8 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     // ---- K2b: destination queries (count / scan / fill) ---------------------------------------
     DevBuf<uint32_t> cand_count;
     DevBuf<int64_t> cand_off;
-    CRG_TRY(cand_count.alloc((size_t)nd + 1, st));
-    CRG_TRY(cand_off.alloc((size_t)nd + 1, st));
+    CRG_TRY(cand_count.alloc_tmp((size_t)nd + 1, st));
+    CRG_TRY(cand_off.alloc_tmp((size_t)nd + 1, st));
     if (nd) bp_query_kernel<DIM, false><<<ceil_div(nd, 128), 128, 0, st>>>(
         gd.view, gd.diam.p, P, bin_start.p, entries.p, big_src.p, n_big_src, ns, cand_count.p, nullptr, nullptr,
         big_dst.p, counters.p + 1);
@@ -494,7 +535,8 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     if (n_cand >= ((int64_t)1 << 32))
         return set_error(CRG_ERR_NOMEM, "candidate pair count %lld exceeds 2^32", (long long)n_cand);
     DevBuf<int2> pairs;
-    CRG_TRY(pairs.alloc((size_t)n_cand, st));
+    if (R->opts.keep_candidates) CRG_TRY(pairs.alloc((size_t)n_cand, st));   // outlives the build
+    else CRG_TRY(pairs.alloc_tmp((size_t)n_cand, st));
     if (nd) bp_query_kernel<DIM, true><<<ceil_div(nd, 128), 128, 0, st>>>(
         gd.view, gd.diam.p, P, bin_start.p, entries.p, big_src.p, n_big_src, ns, nullptr, cand_off.p, pairs.p, nullptr,
         nullptr);
@@ -510,33 +552,44 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     // ---- K3: clip + area, compaction ------------------------------------------------------------
     DevBuf<uint64_t> coo_key;
     DevBuf<double> coo_val;
-    DevBuf<unsigned long long> nkeep;
-    CRG_TRY(coo_key.alloc((size_t)n_cand, st));
-    CRG_TRY(coo_val.alloc((size_t)n_cand, st));
-    CRG_TRY(nkeep.alloc(1, st));
-    CRG_CUDA(cudaMemsetAsync(nkeep.p, 0, sizeof(unsigned long long), st));
+    DevBuf<double> pair_area;
+    DevBuf<uint32_t> tile_count;
+    const int64_t ntiles = (n_cand + CLIP_TILE - 1) / CLIP_TILE;
+    uint32_t h_keep = 0;
     if (n_cand > 0) {
+        CRG_TRY(pair_area.alloc_tmp((size_t)n_cand, st));
+        CRG_TRY(tile_count.alloc_tmp((size_t)ntiles + 1, st));
+        CRG_CUDA(cudaMemsetAsync(tile_count.p, 0, sizeof(uint32_t) * ((size_t)ntiles + 1), st));
+        static const bool allow_quad = !(getenv("CRG_CLIP_QUAD") && atoi(getenv("CRG_CLIP_QUAD")) == 0);
         const bool fixed4 = !dst->offsets && !src->offsets && dst->nv <= 4 && src->nv <= 4;
-        if (fixed4) {
-            constexpr int NT = 128, MW = 8;
-            const size_t smem = sizeof(double) * 2 * MW * DIM * NT;
-            auto kern = clip_kernel<DIM, NT, MW>;
-            CRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<ceil_div(n_cand, NT), NT, smem, st>>>(gd.view, gs.view, pairs.p, n_cand, r2, R->opts.area_threshold,
-                                                         coo_key.p, coo_val.p, nkeep.p);
-        } else {
-            constexpr int NT = 64, MW = 2 * CRG_MAX_VERTS;
-            const size_t smem = sizeof(double) * 2 * MW * DIM * NT;
-            auto kern = clip_kernel<DIM, NT, MW>;
-            CRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<ceil_div(n_cand, NT), NT, smem, st>>>(gd.view, gs.view, pairs.p, n_cand, r2, R->opts.area_threshold,
-                                                         coo_key.p, coo_val.p, nkeep.p);
-        }
+        const bool quad = allow_quad && fixed4 && dst->nv == 4 && src->nv == 4 &&
+                          ((uintptr_t)gd.view.verts % 16 == 0) && ((uintptr_t)gs.view.verts % 16 == 0);
+#define CRG_CLIP(NT_, MW_, QUAD_, NBUF_)                                                                              \
+    do {                                                                                                              \
+        const size_t smem = sizeof(double) * NBUF_ * MW_ * DIM * NT_;                                                 \
+        auto kern = clip_kernel<DIM, NT_, MW_, QUAD_>;                                                                \
+        CRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+        kern<<<ceil_div(n_cand, NT_), NT_, smem, st>>>(gd.view, gs.view, pairs.p, n_cand, R->opts.area_threshold,     \
+                                                       pair_area.p, tile_count.p);                                    \
+    } while (0)
+        if (quad) CRG_CLIP(128, 8, true, 1);
+        else if (fixed4) CRG_CLIP(128, 8, false, 2);
+        else CRG_CLIP(64, 2 * CRG_MAX_VERTS, false, 2);
+#undef CRG_CLIP
         CRG_LAUNCH_CHECK();
+        CRG_TRY((exclusive_scan<uint32_t, uint32_t>(tile_count.p, ntiles, tile_count.p, st)));
+        CRG_CUDA(cudaMemcpyAsync(&h_keep, tile_count.p + ntiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CRG_CUDA(cudaStreamSynchronize(st));
+        CRG_TRY(coo_key.alloc_tmp((size_t)h_keep, st));
+        CRG_TRY(coo_val.alloc_tmp((size_t)h_keep, st));
+        compact_pairs_kernel<<<(unsigned)ntiles, 256, 0, st>>>(pairs.p, pair_area.p, n_cand, tile_count.p, r2, coo_key.p,
+                                                              coo_val.p);
+        CRG_LAUNCH_CHECK();
+        pair_area.release();
+    } else {
+        CRG_TRY(coo_key.alloc_tmp(1, st));
+        CRG_TRY(coo_val.alloc_tmp(1, st));
     }
-    unsigned long long h_keep = 0;
-    CRG_CUDA(cudaMemcpyAsync(&h_keep, nkeep.p, sizeof(h_keep), cudaMemcpyDeviceToHost, st));
-    CRG_CUDA(cudaStreamSynchronize(st));
     if (R->opts.keep_candidates) {
         R->cand_pairs = std::move(pairs);
         R->n_cand_kept = n_cand;
@@ -585,6 +638,33 @@ static int device_stream(int dev, cudaStream_t *out) {
     *out = g_dev_stream[dev];
     return CRG_OK;
 }
+
+// Per-device build arena + the mutex that serialises builds on one device.
+static Arena g_arena[64];
+static std::mutex g_build_mutex[64];
+
+struct ArenaScope {
+    std::unique_lock<std::mutex> lock;
+    Arena *a = nullptr;
+    int begin(int dev, cudaStream_t st) {
+        if (dev < 0 || dev >= 64) return CRG_OK;        // no arena: everything falls back to the pool
+        lock = std::unique_lock<std::mutex>(g_build_mutex[dev]);
+        a = &g_arena[dev];
+        if (a->want > a->cap) {                          // the previous build overflowed: grow (rare)
+            CRG_CUDA(cudaStreamSynchronize(st));
+            if (a->base) CRG_CUDA(cudaFree(a->base));
+            a->base = nullptr;
+            const size_t cap = a->want + a->want / 4 + (64u << 20);
+            if (cudaMalloc((void **)&a->base, cap) == cudaSuccess) a->cap = cap;
+            else { cudaGetLastError(); a->base = nullptr; a->cap = 0; }
+        }
+        a->off = 0;
+        a->want = 0;
+        t_arena = a;
+        return CRG_OK;
+    }
+    ~ArenaScope() { t_arena = nullptr; }
+};
 
 static int new_handle(const crg_options *opts, crg_regridder **out, DeviceGuard &guard) {
     CRG_TRY(check_device_available());
@@ -785,8 +865,14 @@ int crg_build(const crg_options *opts, const crg_cells *dst, const crg_cells *sr
     CRG_TRY(new_handle(opts, &R, guard));
     R->n_dst = dst->ncells;
     R->n_src = src->ncells;
-    int rc = opts->manifold == CRG_SPHERICAL ? build_impl<3>(R, dst, src) : build_impl<2>(R, dst, src);
-    if (rc != CRG_OK) { cudaStreamSynchronize(R->stream); destroy_handle(R); return rc; }
+    int rc;
+    {
+        ArenaScope arena;
+        rc = arena.begin(R->device, R->stream);
+        if (rc == CRG_OK) rc = opts->manifold == CRG_SPHERICAL ? build_impl<3>(R, dst, src) : build_impl<2>(R, dst, src);
+        if (rc != CRG_OK) cudaStreamSynchronize(R->stream);
+    }
+    if (rc != CRG_OK) { destroy_handle(R); return rc; }
     *out = R;
     return CRG_OK;
 }
@@ -816,7 +902,7 @@ int crg_build_from_coo(const crg_options *opts, int64_t n_dst, int64_t n_src, in
         DevBuf<uint64_t> keys;
         DevBuf<double> vals;
         const size_t n1 = (size_t)(nnz > 0 ? nnz : 1);
-        CRG_TRY(dr.alloc(n1, st)); CRG_TRY(dc.alloc(n1, st)); CRG_TRY(keys.alloc(n1, st)); CRG_TRY(vals.alloc(n1, st));
+        CRG_TRY(dr.alloc_tmp(n1, st)); CRG_TRY(dc.alloc_tmp(n1, st)); CRG_TRY(keys.alloc_tmp(n1, st)); CRG_TRY(vals.alloc_tmp(n1, st));
         if (nnz) {
             CRG_CUDA(cudaMemcpyAsync(dr.p, dst_idx, sizeof(int64_t) * nnz, cudaMemcpyDefault, st));
             CRG_CUDA(cudaMemcpyAsync(dc.p, src_idx, sizeof(int64_t) * nnz, cudaMemcpyDefault, st));
@@ -843,8 +929,14 @@ int crg_build_from_coo(const crg_options *opts, int64_t n_dst, int64_t n_src, in
         S.ms_total = now_ms() - t0;
         return CRG_OK;
     };
-    int rc = body();
-    if (rc != CRG_OK) { cudaStreamSynchronize(R->stream); destroy_handle(R); return rc; }
+    int rc;
+    {
+        ArenaScope arena;
+        rc = arena.begin(R->device, R->stream);
+        if (rc == CRG_OK) rc = body();
+        if (rc != CRG_OK) cudaStreamSynchronize(R->stream);
+    }
+    if (rc != CRG_OK) { destroy_handle(R); return rc; }
     *out = R;
     return CRG_OK;
 }

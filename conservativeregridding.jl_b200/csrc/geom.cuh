@@ -209,4 +209,117 @@ __device__ double clip_pair_area(const CellsView &gs, int64_t s, const CellsView
     }
 }
 
+
+// ------------------------------------------------------------------------------------
+// Fast path: quadrilateral x quadrilateral (every structured grid of BASELINE.json).
+//   * the clip cell lives in registers (edge loop fully unrolled, static indexing),
+//   * the working polygon is clipped IN PLACE in one shared-memory buffer of 8 slots: an
+//     output vertex can land at most one slot ahead of the next input vertex (two with
+//     round-off-induced double crossings), so the next two input vertices are carried in
+//     registers -- half the shared memory of the ping-pong version, twice the occupancy,
+//   * cells are fetched with 16-byte loads.
+// ------------------------------------------------------------------------------------
+template <int DIM>
+__device__ __forceinline__ void load_quad(const double *__restrict__ p, bool flip, double (&v)[4][DIM]) {
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    double t[4 * DIM];
+#pragma unroll
+    for (int i = 0; i < 2 * DIM; ++i) { const double2 d = __ldg(q + i); t[2 * i] = d.x; t[2 * i + 1] = d.y; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) v[i][k] = flip ? t[(3 - i) * DIM + k] : t[i * DIM + k];
+}
+
+template <int DIM, int NT>
+__device__ double clip_quad_area(const CellsView &gs, int64_t s, const CellsView &gc, int64_t c,
+                                 double *smem /* 8 * DIM * NT doubles */) {
+    constexpr int MAXW = 8;
+    PolyBuf<DIM, NT, MAXW> cur{smem + threadIdx.x};
+    double cv[4][DIM];
+    {
+        double sv[4][DIM];
+        load_quad<DIM>(gs.verts + s * 4 * DIM, gs.flip && gs.flip[s], sv);
+        load_quad<DIM>(gc.verts + c * 4 * DIM, gc.flip && gc.flip[c], cv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) cur.set(i, k, sv[i][k]);
+    }
+    int m = 4;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        if (m == 0) break;
+        const double *u = cv[e], *v = cv[(e + 1) & 3];
+        double nx, ny, nz = 0.0, h0 = 0.0;
+        if (DIM == 3) {
+            nx = u[1] * v[2] - u[2] * v[1]; ny = u[2] * v[0] - u[0] * v[2]; nz = u[0] * v[1] - u[1] * v[0];
+            if (nx == 0.0 && ny == 0.0 && nz == 0.0) continue;   // zero-length edge (pole cells)
+        } else {
+            const double ex = v[0] - u[0], ey = v[1] - u[1];
+            if (ex == 0.0 && ey == 0.0) continue;
+            nx = -ey; ny = ex;
+            h0 = -(nx * u[0] + ny * u[1]);
+        }
+        // registers: L = last vertex, (q1, q2) = the next two input vertices
+        const double Lx = cur.get(m - 1, 0), Ly = cur.get(m - 1, 1), Lz = DIM == 3 ? cur.get(m - 1, 2) : 0.0;
+        double q1x = cur.get(0, 0), q1y = cur.get(0, 1), q1z = DIM == 3 ? cur.get(0, 2) : 0.0;
+        double q2x = Lx, q2y = Ly, q2z = Lz;
+        if (m > 2) { q2x = cur.get(1, 0); q2y = cur.get(1, 1); q2z = DIM == 3 ? cur.get(1, 2) : 0.0; }
+        double px = Lx, py = Ly, pz = Lz;
+        double dp = DIM == 3 ? fma(nx, px, fma(ny, py, nz * pz)) : fma(nx, px, fma(ny, py, h0));
+        int mo = 0;
+        for (int i = 0; i < m; ++i) {
+            const double qx = q1x, qy = q1y, qz = q1z;
+            q1x = q2x; q1y = q2y; q1z = q2z;
+            if (i + 2 < m - 1) { q2x = cur.get(i + 2, 0); q2y = cur.get(i + 2, 1); q2z = DIM == 3 ? cur.get(i + 2, 2) : 0.0; }
+            else { q2x = Lx; q2y = Ly; q2z = Lz; }
+            const double dq = DIM == 3 ? fma(nx, qx, fma(ny, qy, nz * qz)) : fma(nx, qx, fma(ny, qy, h0));
+            const bool in_p = dp >= 0.0, in_q = dq >= 0.0;
+            if (in_p != in_q) {
+                const double t = dp / (dp - dq);
+                double rx = fma(t, qx - px, px), ry = fma(t, qy - py, py), rz = fma(t, qz - pz, pz);
+                if (DIM == 3) {
+                    const double inv = rsqrt(rx * rx + ry * ry + rz * rz);
+                    rx *= inv; ry *= inv; rz *= inv;
+                }
+                if (mo <= i + 2 && mo < MAXW) {
+                    cur.set(mo, 0, rx); cur.set(mo, 1, ry);
+                    if (DIM == 3) cur.set(mo, 2, rz);
+                    ++mo;
+                }
+            }
+            if (in_q && mo <= i + 2 && mo < MAXW) {
+                cur.set(mo, 0, qx); cur.set(mo, 1, qy);
+                if (DIM == 3) cur.set(mo, 2, qz);
+                ++mo;
+            }
+            dp = dq; px = qx; py = qy; pz = qz;
+        }
+        m = mo;
+    }
+    if (m < 3) return 0.0;
+    if (DIM == 3) {
+        ExcessAcc acc;
+        const d3 a = {cur.get(0, 0), cur.get(0, 1), cur.get(0, 2)};
+        d3 b = {cur.get(1, 0), cur.get(1, 1), cur.get(1, 2)};
+        for (int i = 2; i < m; ++i) {
+            const d3 cc = {cur.get(i, 0), cur.get(i, 1), cur.get(i, 2)};
+            acc.add_triangle(a, b, cc);
+            b = cc;
+        }
+        return acc.area();
+    } else {
+        double sarea = 0.0;
+        const double x0 = cur.get(0, 0), y0 = cur.get(0, 1);
+        double ax = cur.get(1, 0) - x0, ay = cur.get(1, 1) - y0;
+        for (int i = 2; i < m; ++i) {
+            const double bx = cur.get(i, 0) - x0, by = cur.get(i, 1) - y0;
+            sarea += ax * by - ay * bx;
+            ax = bx; ay = by;
+        }
+        return 0.5 * sarea;
+    }
+}
+
 }  // namespace crg

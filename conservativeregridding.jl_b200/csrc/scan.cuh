@@ -76,7 +76,7 @@ int exclusive_scan(const Tin *in, int64_t n, Tout *out, cudaStream_t st) {
         return CRG_OK;
     }
     DevBuf<Tout> sums;
-    CRG_TRY(sums.alloc((size_t)ntiles + 1, st));
+    CRG_TRY(sums.alloc_tmp((size_t)ntiles + 1, st));
     scan_reduce_kernel<Tin, Tout><<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(in, n, sums.p);
     CRG_LAUNCH_CHECK();
     CRG_TRY((exclusive_scan<Tout, Tout>(sums.p, ntiles, sums.p, st)));

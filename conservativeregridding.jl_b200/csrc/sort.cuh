@@ -103,7 +103,7 @@ inline int radix_sort_pairs(uint64_t *keys_a, uint64_t *vals_a, uint64_t *keys_b
         if (n >= ((int64_t)1 << 32)) return set_error(CRG_ERR_NOMEM, "radix sort: %lld elements exceed 2^32", (long long)n);
         const int ntiles = (int)((n + RS_TILE - 1) / RS_TILE);
         DevBuf<uint32_t> hist;
-        CRG_TRY(hist.alloc((size_t)RS_RADIX * ntiles + 1, st));
+        CRG_TRY(hist.alloc_tmp((size_t)RS_RADIX * ntiles + 1, st));
         uint64_t *ki = keys_a, *vi = vals_a, *ko = keys_b, *vo = vals_b;
         for (int shift = bit_lo; shift < bit_hi; shift += 8) {
             rs_upsweep_kernel<<<ntiles, RS_THREADS, 0, st>>>(ki, n, shift, ntiles, hist.p);
