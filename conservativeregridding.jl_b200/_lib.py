@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(CSRC, "libcrgb200.so")
 SOURCES = ["crg_b200.cu"]
-HEADERS = ["common.cuh", "scan.cuh", "sort.cuh", "geom.cuh", "broadphase.cuh", "kernels.cuh", "sell.cuh"]
+HEADERS = ["common.cuh", "scan.cuh", "sort.cuh", "geom.cuh", "gridgen.cuh", "broadphase.cuh", "kernels.cuh", "sell.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -31,7 +31,7 @@ EXPORTS = [
     "crg_options_init", "crg_build", "crg_build_from_coo", "crg_free", "crg_dims", "crg_stats", "crg_areas",
     "crg_export_csc", "crg_export_csr", "crg_candidates", "crg_normalize", "crg_apply", "crg_apply_async",
     "crg_set_stream", "crg_synchronize", "crg_apply_bytes", "crg_last_error", "crg_device_count", "crg_version",
-    "crg_fp64_peak", "crg_launch_count",
+    "crg_fp64_peak", "crg_launch_count", "crg_build_grids", "crg_grid_ncells", "crg_grid_cells",
 ]
 
 
@@ -50,6 +50,14 @@ class Options(C.Structure):
 class Cells(C.Structure):
     _fields_ = [("verts", C.c_void_p), ("offsets", C.c_void_p), ("ncells", C.c_int64), ("nv", C.c_int32),
                 ("reserved", C.c_int32)]
+
+
+class GridDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("flags", C.c_int32), ("cells", Cells), ("n1", C.c_int64), ("n2", C.c_int64),
+                ("p", C.c_double * 4), ("lat_deg", C.c_void_p)]
+
+
+GRID_CELLS, GRID_LONLAT, GRID_HEALPIX, GRID_FULL_RING, GRID_CUBED_SPHERE = 0, 1, 2, 3, 4
 
 
 class BuildStats(C.Structure):
@@ -111,6 +119,9 @@ def lib():
     L.crg_version.restype = C.c_char_p
     L.crg_options_init.argtypes = [P(Options)]
     L.crg_build.argtypes = [P(Options), P(Cells), P(Cells), P(vp)]
+    L.crg_build_grids.argtypes = [P(Options), P(GridDesc), P(GridDesc), P(vp)]
+    L.crg_grid_ncells.argtypes = [P(GridDesc), P(i64)]
+    L.crg_grid_cells.argtypes = [P(GridDesc), i32, vp]
     L.crg_build_from_coo.argtypes = [P(Options), i64, i64, i64, vp, vp, vp, vp, vp, P(vp)]
     L.crg_free.argtypes = [vp]
     L.crg_dims.argtypes = [vp, P(i64), P(i64), P(i64)]

@@ -11,6 +11,7 @@
 #include "broadphase.cuh"
 #include "common.cuh"
 #include "geom.cuh"
+#include "gridgen.cuh"
 #include "kernels.cuh"
 #include "scan.cuh"
 #include "sort.cuh"
@@ -813,6 +814,57 @@ static int export_csr_matrix(const crg_regridder *R, const Csr &M, int32_t base,
     return CRG_OK;
 }
 
+// ---- described grids ---------------------------------------------------------------------------
+static int grid_ncells(const crg_grid *g, int64_t *n) {
+    if (!g) return set_error(CRG_ERR_INVALID, "null grid");
+    switch (g->kind) {
+        case CRG_GRID_CELLS: *n = g->cells.ncells; return CRG_OK;
+        case CRG_GRID_LONLAT:
+        case CRG_GRID_FULL_RING:
+            if (g->n1 < 1 || g->n2 < 1) return set_error(CRG_ERR_INVALID, "grid: n1, n2 must be positive");
+            if (g->kind == CRG_GRID_FULL_RING && !g->lat_deg) return set_error(CRG_ERR_INVALID, "full-ring grid: null lat_deg");
+            *n = g->n1 * g->n2; return CRG_OK;
+        case CRG_GRID_HEALPIX:
+            if (g->n1 < 1 || (g->n1 & (g->n1 - 1)) || g->n1 > (1 << 13)) return set_error(CRG_ERR_INVALID, "healpix: nside must be a power of two <= 8192");
+            *n = 12 * g->n1 * g->n1; return CRG_OK;
+        case CRG_GRID_CUBED_SPHERE:
+            if (g->n1 < 1) return set_error(CRG_ERR_INVALID, "cubed sphere: n must be positive");
+            *n = 6 * g->n1 * g->n1; return CRG_OK;
+        default: return set_error(CRG_ERR_INVALID, "unknown grid kind %d", g->kind);
+    }
+}
+
+// Generate the [ncells][4][3] vertices of a described grid into `verts` (device memory).
+static int generate_grid(const crg_grid *g, int64_t n, double *verts, cudaStream_t st) {
+    if (n == 0) return CRG_OK;
+    const int nblk = ceil_div(n, 256);
+    switch (g->kind) {
+        case CRG_GRID_LONLAT:
+            gen_lonlat_kernel<<<nblk, 256, 0, st>>>(g->n1, g->n2, g->p[0], g->p[1], g->p[2], g->p[3], verts);
+            break;
+        case CRG_GRID_HEALPIX:
+            gen_healpix_kernel<<<nblk, 256, 0, st>>>(g->n1, g->flags & 1, verts);
+            break;
+        case CRG_GRID_CUBED_SPHERE:
+            gen_cubed_sphere_kernel<<<nblk, 256, 0, st>>>(g->n1, verts);
+            break;
+        case CRG_GRID_FULL_RING: {
+            const double *lat = g->lat_deg;
+            DevBuf<double> dlat;
+            if (!is_device_ptr(lat)) {
+                CRG_TRY(dlat.alloc_tmp((size_t)g->n2, st));
+                CRG_CUDA(cudaMemcpyAsync(dlat.p, lat, sizeof(double) * (size_t)g->n2, cudaMemcpyHostToDevice, st));
+                lat = dlat.p;
+            }
+            gen_full_ring_kernel<<<nblk, 256, 0, st>>>(g->n1, g->n2, g->p[0], lat, verts);
+            break;
+        }
+        default: return set_error(CRG_ERR_INVALID, "grid kind %d cannot be generated", g->kind);
+    }
+    CRG_LAUNCH_CHECK();
+    return CRG_OK;
+}
+
 }  // namespace crg
 
 // =============================================================================================
@@ -870,6 +922,75 @@ int crg_build(const crg_options *opts, const crg_cells *dst, const crg_cells *sr
         ArenaScope arena;
         rc = arena.begin(R->device, R->stream);
         if (rc == CRG_OK) rc = opts->manifold == CRG_SPHERICAL ? build_impl<3>(R, dst, src) : build_impl<2>(R, dst, src);
+        if (rc != CRG_OK) cudaStreamSynchronize(R->stream);
+    }
+    if (rc != CRG_OK) { destroy_handle(R); return rc; }
+    *out = R;
+    return CRG_OK;
+}
+
+int crg_grid_ncells(const crg_grid *g, int64_t *ncells) {
+    if (!ncells) return set_error(CRG_ERR_INVALID, "null argument");
+    return grid_ncells(g, ncells);
+}
+
+int crg_grid_cells(const crg_grid *g, int32_t device, double *verts) {
+    int64_t n = 0;
+    CRG_TRY(grid_ncells(g, &n));
+    if (!verts) return set_error(CRG_ERR_INVALID, "null verts");
+    if (g->kind == CRG_GRID_CELLS) return set_error(CRG_ERR_INVALID, "grid is already explicit");
+    CRG_TRY(check_device_available());
+    DeviceGuard guard;
+    CRG_TRY(guard.set(device));
+    int dev = 0;
+    CRG_CUDA(cudaGetDevice(&dev));
+    cudaStream_t st;
+    CRG_TRY(device_stream(dev, &st));
+    if (is_device_ptr(verts)) {
+        CRG_TRY(generate_grid(g, n, verts, st));
+    } else {
+        DevBuf<double> tmp;
+        CRG_TRY(tmp.alloc((size_t)n * 12, st));
+        CRG_TRY(generate_grid(g, n, tmp.p, st));
+        CRG_CUDA(cudaMemcpyAsync(verts, tmp.p, sizeof(double) * (size_t)n * 12, cudaMemcpyDeviceToHost, st));
+    }
+    CRG_CUDA(cudaStreamSynchronize(st));
+    return CRG_OK;
+}
+
+int crg_build_grids(const crg_options *opts, const crg_grid *dst, const crg_grid *src, crg_regridder **out) {
+    if (!opts || !out || !dst || !src) return set_error(CRG_ERR_INVALID, "crg_build_grids: null argument");
+    *out = nullptr;
+    if (dst->kind == CRG_GRID_CELLS && src->kind == CRG_GRID_CELLS) return crg_build(opts, &dst->cells, &src->cells, out);
+    if (opts->manifold != CRG_SPHERICAL) return set_error(CRG_ERR_INVALID, "crg_build_grids: described grids live on the sphere");
+    if (!(opts->radius > 0.0)) return set_error(CRG_ERR_INVALID, "crg_build_grids: radius must be positive");
+    int64_t nd = 0, ns = 0;
+    CRG_TRY(grid_ncells(dst, &nd));
+    CRG_TRY(grid_ncells(src, &ns));
+    if (dst->kind == CRG_GRID_CELLS) CRG_TRY(validate_cells(&dst->cells, "dst"));
+    if (src->kind == CRG_GRID_CELLS) CRG_TRY(validate_cells(&src->cells, "src"));
+    if (nd >= ((int64_t)1 << 31) || ns >= ((int64_t)1 << 31)) return set_error(CRG_ERR_INVALID, "grid too large");
+    DeviceGuard guard;
+    crg_regridder *R = nullptr;
+    CRG_TRY(new_handle(opts, &R, guard));
+    R->n_dst = nd;
+    R->n_src = ns;
+    int rc;
+    {
+        ArenaScope arena;
+        rc = arena.begin(R->device, R->stream);
+        DevBuf<double> vd, vs;
+        crg_cells cd = dst->cells, cs = src->cells;
+        auto materialise = [&](const crg_grid *g, int64_t n, DevBuf<double> &buf, crg_cells *c) -> int {
+            if (g->kind == CRG_GRID_CELLS) return CRG_OK;
+            CRG_TRY(buf.alloc_tmp((size_t)(n > 0 ? n : 1) * 12, R->stream));
+            CRG_TRY(generate_grid(g, n, buf.p, R->stream));
+            c->verts = buf.p; c->offsets = nullptr; c->ncells = n; c->nv = 4; c->reserved = 0;
+            return CRG_OK;
+        };
+        if (rc == CRG_OK) rc = materialise(dst, nd, vd, &cd);
+        if (rc == CRG_OK) rc = materialise(src, ns, vs, &cs);
+        if (rc == CRG_OK) rc = build_impl<3>(R, &cd, &cs);
         if (rc != CRG_OK) cudaStreamSynchronize(R->stream);
     }
     if (rc != CRG_OK) { destroy_handle(R); return rc; }

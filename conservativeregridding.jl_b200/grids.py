@@ -80,6 +80,69 @@ class Grid:
         return self.verts[self.offsets[i]:self.offsets[i + 1]]
 
 
+@dataclass
+class GridSpec:
+    """A structured grid described by a few numbers; its cell vertices are generated ON THE DEVICE
+    inside ``crg_build_grids`` (csrc/gridgen.cuh), so no vertex soup is built or uploaded by the
+    host.  ``kind``: "lonlat" | "healpix" | "full_ring" | "cubed_sphere" (include/crg_b200.h).
+    ``materialize()`` gives the equivalent host :class:`Grid` (same conventions, same order)."""
+
+    kind: str
+    n1: int
+    n2: int = 0
+    p: tuple = (0.0, 0.0, 0.0, 0.0)
+    flags: int = 0
+    lat_deg: Optional[np.ndarray] = None
+    radius: float = 1.0
+    name: str = ""
+    manifold: int = 1
+
+    @property
+    def ncells(self) -> int:
+        if self.kind == "healpix":
+            return 12 * self.n1 * self.n1
+        if self.kind == "cubed_sphere":
+            return 6 * self.n1 * self.n1
+        return self.n1 * self.n2
+
+    def materialize(self) -> "Grid":
+        if self.kind == "lonlat":
+            return lonlat_grid(self.n1, self.n2, *self.p, radius=self.radius)
+        if self.kind == "healpix":
+            return healpix_grid(self.n1, "nested" if self.flags & 1 else "ring", radius=self.radius)
+        if self.kind == "full_ring":
+            return full_ring_grid(self.lat_deg, self.n1, self.p[0], self.radius, self.name or "fullring")
+        if self.kind == "cubed_sphere":
+            return cubed_sphere_grid(self.n1, radius=self.radius)
+        raise ValueError(self.kind)
+
+
+def lonlat_spec(nlon, nlat, lon0=0.0, lon1=360.0, lat0=-90.0, lat1=90.0, radius=1.0) -> GridSpec:
+    return GridSpec("lonlat", nlon, nlat, (float(lon0), float(lon1), float(lat0), float(lat1)), 0, None, radius,
+                    f"lonlat{nlon}x{nlat}")
+
+
+def healpix_spec(nside, order="ring", radius=1.0) -> GridSpec:
+    assert nside >= 1 and (nside & (nside - 1)) == 0
+    return GridSpec("healpix", nside, 0, (0.0,) * 4, 1 if order == "nested" else 0, None, radius, f"healpix{nside}{order}")
+
+
+def full_gaussian_spec(nlat_half, radius=1.0) -> GridSpec:
+    return GridSpec("full_ring", 4 * nlat_half, 2 * nlat_half, (0.0, 0.0, 0.0, 0.0), 0,
+                    np.ascontiguousarray(gaussian_latitudes(2 * nlat_half)), radius, f"F{nlat_half}")
+
+
+def full_clenshaw_spec(nlat_half, radius=1.0) -> GridSpec:
+    nlat = 2 * nlat_half - 1
+    latd = 90.0 - 90.0 * (np.arange(1, nlat + 1) / nlat_half)
+    return GridSpec("full_ring", 4 * nlat_half, nlat, (0.0, 0.0, 0.0, 0.0), 0, np.ascontiguousarray(latd), radius,
+                    f"FullClenshaw{nlat_half}")
+
+
+def cubed_sphere_spec(n, radius=1.0) -> GridSpec:
+    return GridSpec("cubed_sphere", n, 0, (0.0,) * 4, 0, None, radius, f"C{n}")
+
+
 # ----------------------------------------------------------------------------
 # degree-exact trigonometry
 # ----------------------------------------------------------------------------

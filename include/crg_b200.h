@@ -84,6 +84,33 @@ typedef struct crg_cells {
     int32_t reserved;
 } crg_cells;
 
+/* A grid given either explicitly (cells) or by a few numbers, in which case the cell vertices are
+ * generated on the device, straight into the build's scratch memory (no host vertex soup, no
+ * upload).  Cell conventions and field-linear order are the reference's:
+ *   CRG_GRID_LONLAT       Oceananigans LatitudeLongitudeGrid   ext/ConservativeRegriddingOceananigansExt.jl:23-60,242-264
+ *                         n1 = nlon, n2 = nlat, p = {lon0, lon1, lat0, lat1} degrees; lon fastest, S -> N
+ *   CRG_GRID_HEALPIX      HealpixMap                           ext/ConservativeRegriddingHealpixExt.jl:76-90,138-167
+ *                         n1 = nside (power of two), flags = 0 ring order | 1 nested order
+ *   CRG_GRID_FULL_RING    RingGrids AbstractFullGrid           ext/ConservativeRegriddingRingGridsExt.jl:22-50
+ *                         n1 = nlon, n2 = nlat, p[0] = longitude of the first point, lat_deg = the nlat
+ *                         ring latitudes in degrees, north -> south (host or device pointer)
+ *   CRG_GRID_CUBED_SPHERE equiangular gnomonic cubed sphere, n1 = cells per panel edge; 6 panels,
+ *                         panel-major (each panel is a CellBasedGrid, src/trees/grids.jl:57-85)      */
+#define CRG_GRID_CELLS 0
+#define CRG_GRID_LONLAT 1
+#define CRG_GRID_HEALPIX 2
+#define CRG_GRID_FULL_RING 3
+#define CRG_GRID_CUBED_SPHERE 4
+
+typedef struct crg_grid {
+    int32_t kind;
+    int32_t flags;
+    crg_cells cells;       /* kind == CRG_GRID_CELLS */
+    int64_t n1, n2;
+    double p[4];
+    const double *lat_deg;
+} crg_grid;
+
 /* Counters and per-phase device times (CUDA events, milliseconds) of the last build. */
 typedef struct crg_build_stats {
     int64_t n_dst, n_src;
@@ -102,6 +129,14 @@ int crg_options_init(crg_options *opts);
 
 int crg_build(const crg_options *opts, const crg_cells *dst, const crg_cells *src,
               crg_regridder **out);
+
+/* Same as crg_build with grids that may be described instead of listed (spherical manifold). */
+int crg_build_grids(const crg_options *opts, const crg_grid *dst, const crg_grid *src, crg_regridder **out);
+
+/* Number of cells of a grid; and its cell vertices ([ncells][4][3] doubles, host or device `verts`)
+ * generated on `device` -- what crg_build_grids feeds to the build (tests / export).             */
+int crg_grid_ncells(const crg_grid *g, int64_t *ncells);
+int crg_grid_cells(const crg_grid *g, int32_t device, double *verts);
 
 /* Assemble from explicit (dst_idx, src_idx, area) triples (0-based; duplicates are summed;
  * non-positive areas must already be dropped by the caller, intersection_areas.jl:24).

