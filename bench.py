@@ -261,7 +261,7 @@ def main():
         if record: e[3].record()
         flush.sum()
         if record: e[4].record()
-        xb = S.regrid(y, transpose=True, broadcast=False)           # all-gather
+        xb = S.regrid(y, transpose=True)                            # local A_r^T y_r + NCCL all-reduce
         if record: e[5].record()
         state["R"], state["y"], state["xb"] = S, y, xb
         return e
@@ -330,7 +330,7 @@ def main():
         stats = R.intersections.stats()
     else:
         da, sa = R.dst_areas, R.src_areas
-        stats = R.fwd.stats
+        stats = R.local.stats
     cons = abs(float((y * da).sum() / (x_dev * sa).sum()) - 1.0) if rank == 0 or world == 1 else 0.0
     cons_T = abs(float((xb * sa).sum() / (y * da).sum()) - 1.0)
     assert cons < 1e-11 and cons_T < 1e-11, (cons, cons_T)
@@ -348,7 +348,7 @@ def main():
             by_t = transpose(R).intersections.apply_bytes(1, True)
         else:
             lo, hi = R.dst_bounds[0]
-            by_f = 12 * R.fwd.nnz + 4 * (hi - lo + 1) + 8 * (hi - lo) + 8 * (n_src + hi - lo)
+            by_f = 12 * R.local.nnz + 4 * (hi - lo + 1) + 8 * (hi - lo) + 8 * (n_src + hi - lo)
             by_t = None
         apply_f_gbs = by_f / (fwd_ms * 1e-3) / 1e9 if world == 1 else None
         apply_t_gbs = by_t / (bwd_ms * 1e-3) / 1e9 if world == 1 else None
@@ -457,7 +457,7 @@ def main():
             S = ShardedRegridder(dd, sd, local_factory=factory, device=dev)
             xd = xh_t.to(dev, non_blocking=True) if rank == 0 else None
             y_ = S.regrid(xd)
-            xb_ = S.regrid(y_, transpose=True, broadcast=False)
+            xb_ = S.regrid(y_, transpose=True)
             return y_.cpu(), xb_.cpu()
         step_e2e()
         barrier()

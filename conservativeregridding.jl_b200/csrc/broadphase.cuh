@@ -3,7 +3,7 @@
 // machinery of src/trees/grids.jl:245-287).
 //
 // Spherical cells are binned on the six faces of a cube in *equiangular gnomonic*
-// coordinates (alpha, beta) = (atan(b/a), atan(c/a)): the gnomonic map sends great-circle
+// coordinates (alpha, beta) = (f(b/a), f(c/a)), f(u) = u/sqrt(1+u^2): the gnomonic map sends great-circle
 // arcs to straight segments, so the exact bounding box of a great-circle polygon on a face
 // is the bounding box of its projected vertices -- no arc-bulge terms, no poles, no date
 // line.  Each face's bin domain is extended by a margin >= the largest destination cell, so
@@ -85,17 +85,23 @@ __device__ __forceinline__ bool cell_face_qbox(const double *p, int n, int face,
                                                bool *clamped) {
     double a0 = 1e300, a1 = -1e300, b0 = 1e300, b1 = -1e300;
     if (DIM == 3) {
+        // face coordinates f(u) = u / sqrt(1 + u^2) = sin(atan u) of the gnomonic u = b/a, v = c/a: any
+        // monotone map of u keeps "box of the projected vertices = box of the polygon"; this one is a
+        // few FP32 instructions (the FP64 atan version made the binning kernels FP64-bound).  FP32
+        // round-off (< 3e-7) is covered by the box inflation P.eps = 1e-6.
         const int ax = face >> 1;
-        const double sg = (face & 1) ? -1.0 : 1.0;
+        const float sg = (face & 1) ? -1.f : 1.f;
         const int bx = ax == 2 ? 0 : ax + 1, cx = bx == 2 ? 0 : bx + 1;
+        float fa0 = 2.f, fa1 = -2.f, fb0 = 2.f, fb1 = -2.f;
         for (int i = 0; i < n; ++i) {
-            const double w = sg * p[3 * i + ax];
-            if (!(w > BP_MIN_W)) return false;
-            const double iw = 1.0 / w;
-            const double al = atan(p[3 * i + bx] * iw), be = atan(p[3 * i + cx] * iw);
-            a0 = fmin(a0, al); a1 = fmax(a1, al);
-            b0 = fmin(b0, be); b1 = fmax(b1, be);
+            const float w = sg * (float)p[3 * i + ax];
+            if (!(w > (float)BP_MIN_W)) return false;
+            const float u = (float)p[3 * i + bx] / w, v = (float)p[3 * i + cx] / w;
+            const float al = u * rsqrtf(fmaf(u, u, 1.f)), be = v * rsqrtf(fmaf(v, v, 1.f));
+            fa0 = fminf(fa0, al); fa1 = fmaxf(fa1, al);
+            fb0 = fminf(fb0, be); fb1 = fmaxf(fb1, be);
         }
+        a0 = fa0; a1 = fa1; b0 = fb0; b1 = fb1;
     } else {
         for (int i = 0; i < n; ++i) {
             const double al = p[2 * i], be = p[2 * i + 1];
@@ -121,17 +127,58 @@ __device__ __forceinline__ const double *cell_ptr(const CellsView &g, int64_t c,
     return g.verts + f * DIM;
 }
 
+// Cell access for the streaming kernels (one thread per cell).  A thread reading its own 96-byte
+// quad touches 12 scattered 8-byte words per warp instruction; for fixed-stride quads each warp
+// instead copies its 32 consecutive cells (3 KB, contiguous) with 16-byte coalesced loads into a
+// padded shared-memory tile and every thread reads its cell from there.  Must be called by all
+// threads of the block (blockDim.x <= 256); returns this thread's cell (shared or global memory).
+constexpr int STAGE_THREADS = 256;
+template <int DIM>
+struct CellStage {
+    static constexpr int CELL = 4 * DIM;          // doubles per quad
+    static constexpr int PAD = CELL + 1;          // padded stride: conflict-free 8-byte reads
+    double tile[STAGE_THREADS * PAD];
+};
+template <int DIM>
+__device__ __forceinline__ const double *stage_cell(const CellsView &g, int64_t c, int *n, CellStage<DIM> &S) {
+    constexpr int CELL = CellStage<DIM>::CELL, PAD = CellStage<DIM>::PAD, CHUNKS = CELL / 2;
+    const bool fast = !g.off && g.nv == 4 && ((uintptr_t)g.verts % 16 == 0);     // block-uniform
+    if (!fast) {
+        if (c >= g.ncells) { *n = 0; return g.verts; }
+        return cell_ptr<DIM>(g, c, n);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t c0 = c - lane;                  // first cell of this warp
+    const int64_t nvalid = g.ncells - c0;         // cells of this warp inside the grid (may be <= 0)
+    double *w = S.tile + wid * 32 * PAD;
+    const double2 *src = reinterpret_cast<const double2 *>(g.verts + c0 * CELL);
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) {
+        const int q = i * 32 + lane;              // 16-byte chunk index inside the warp's 32 cells
+        const int cell = q / CHUNKS, part = q % CHUNKS;
+        if (cell < nvalid) {
+            const double2 v = __ldg(src + q);
+            w[cell * PAD + 2 * part] = v.x;
+            w[cell * PAD + 2 * part + 1] = v.y;
+        }
+    }
+    __syncwarp();
+    *n = c < g.ncells ? 4 : 0;
+    return w + lane * PAD;
+}
+
 // --- bounds: per-cell diameter + grid statistics -----------------------------------------
 template <int DIM>
 __global__ void __launch_bounds__(256) bp_bounds_kernel(CellsView g, float *__restrict__ diam, BPStats *st,
                                                         float big_chord) {
+    __shared__ CellStage<DIM> stage;
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double sum = 0.0, lo0 = 1e300, lo1 = 1e300, hi0 = -1e300, hi1 = -1e300;
     float mx = 0.f;
     unsigned cnt = 0;
+    int n;
+    const double *p = stage_cell<DIM>(g, c, &n, stage);
     if (c < g.ncells) {
-        int n;
-        const double *p = cell_ptr<DIM>(g, c, &n);
         const float d = cell_diameter<DIM>(p, n);
         diam[c] = d;
         if (DIM == 2 || d < big_chord) { sum = d; mx = d; cnt = 1; }
@@ -143,13 +190,27 @@ __global__ void __launch_bounds__(256) bp_bounds_kernel(CellsView g, float *__re
     }
     sum = warp_sum(sum); mx = warp_max(mx); cnt = warp_sum(cnt);
     if (DIM == 2) { lo0 = warp_min(lo0); lo1 = warp_min(lo1); hi0 = warp_max(hi0); hi1 = warp_max(hi1); }
-    if ((threadIdx.x & 31) == 0 && cnt) {
-        atomicAdd(&st->sum_diam, sum);
-        atomicAdd(&st->count, (unsigned long long)cnt);
-        atomic_max_pos_float(&st->max_diam, mx);
-        if (DIM == 2) {
-            atomicMin(&st->lo[0], ordered_bits(lo0)); atomicMin(&st->lo[1], ordered_bits(lo1));
-            atomicMax(&st->hi[0], ordered_bits(hi0)); atomicMax(&st->hi[1], ordered_bits(hi1));
+    // one set of atomics per block (same-address atomics from every warp serialised at the L2)
+    __shared__ double r_sum[8], r_lo0[8], r_lo1[8], r_hi0[8], r_hi1[8];
+    __shared__ float r_mx[8];
+    __shared__ unsigned r_cnt[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { r_sum[wid] = sum; r_mx[wid] = mx; r_cnt[wid] = cnt; r_lo0[wid] = lo0; r_lo1[wid] = lo1; r_hi0[wid] = hi0; r_hi1[wid] = hi1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nw = blockDim.x >> 5;
+        for (int w = 1; w < nw; ++w) {
+            sum += r_sum[w]; mx = fmaxf(mx, r_mx[w]); cnt += r_cnt[w];
+            lo0 = fmin(lo0, r_lo0[w]); lo1 = fmin(lo1, r_lo1[w]); hi0 = fmax(hi0, r_hi0[w]); hi1 = fmax(hi1, r_hi1[w]);
+        }
+        if (cnt) {
+            atomicAdd(&st->sum_diam, sum);
+            atomicAdd(&st->count, (unsigned long long)cnt);
+            atomic_max_pos_float(&st->max_diam, mx);
+            if (DIM == 2) {
+                atomicMin(&st->lo[0], ordered_bits(lo0)); atomicMin(&st->lo[1], ordered_bits(lo1));
+                atomicMax(&st->hi[0], ordered_bits(hi0)); atomicMax(&st->hi[1], ordered_bits(hi1));
+            }
         }
     }
 }
@@ -162,19 +223,19 @@ __global__ void __launch_bounds__(256) bp_bin_kernel(CellsView g, const float *_
                                                      const uint32_t *__restrict__ bin_start,
                                                      int4 *__restrict__ entries, int32_t *__restrict__ big_list,
                                                      uint32_t *__restrict__ big_counter) {
+    __shared__ CellStage<DIM> stage;
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= g.ncells) return;
     int n;
-    const double *p = cell_ptr<DIM>(g, c, &n);
+    const double *p = stage_cell<DIM>(g, c, &n, stage);
+    if (c >= g.ncells) return;
     bool big = DIM == 3 && !(diam[c] < (float)P.big_chord);
-    QBox box[6];
-    bool ok[6];
-    if (!big) {
-        int cover = 0;
+    if (!big) {     // total number of bins the cell would be inserted in (boxes are recomputed below: cheaper
+        int cover = 0;  // than keeping six of them in local memory)
         for (int f = 0; f < P.nfaces; ++f) {
+            QBox b;
             bool cl;
-            ok[f] = cell_face_qbox<DIM>(p, n, f, P, &box[f], &cl);
-            if (ok[f]) cover += ((box[f].x1 >> 4) - (box[f].x0 >> 4) + 1) * ((box[f].y1 >> 4) - (box[f].y0 >> 4) + 1);
+            if (cell_face_qbox<DIM>(p, n, f, P, &b, &cl))
+                cover += ((b.x1 >> 4) - (b.x0 >> 4) + 1) * ((b.y1 >> 4) - (b.y0 >> 4) + 1);
         }
         big = cover > BP_MAX_COVER;
     }
@@ -183,8 +244,9 @@ __global__ void __launch_bounds__(256) bp_bin_kernel(CellsView g, const float *_
         return;
     }
     for (int f = 0; f < P.nfaces; ++f) {
-        if (!ok[f]) continue;
-        const QBox b = box[f];
+        QBox b;
+        bool cl;
+        if (!cell_face_qbox<DIM>(p, n, f, P, &b, &cl)) continue;
         const int4 e = make_int4((int)c, b.x0 | (b.x1 << 16), b.y0 | (b.y1 << 16), 0);
         for (int by = b.y0 >> 4; by <= (b.y1 >> 4); ++by)
             for (int bx = b.x0 >> 4; bx <= (b.x1 >> 4); ++bx) {
@@ -218,10 +280,11 @@ __global__ void __launch_bounds__(128) bp_query_kernel(CellsView g, const float 
                                                        const int64_t *__restrict__ cand_off,
                                                        int2 *__restrict__ pairs, int32_t *__restrict__ big_dst,
                                                        uint32_t *__restrict__ big_dst_counter) {
+    __shared__ CellStage<DIM> stage;
     const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= g.ncells) return;
     int n;
-    const double *p = cell_ptr<DIM>(g, d, &n);
+    const double *p = stage_cell<DIM>(g, d, &n, stage);
+    if (d >= g.ncells) return;
     bool big = DIM == 3 && !(diam[d] < (float)P.big_chord);
     QBox b;
     int f = 0;

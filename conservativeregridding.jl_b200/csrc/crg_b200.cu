@@ -444,8 +444,9 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
         P.nfaces = 6;
         double margin = hst[0].count ? 1.4 * 2.0 * std::asin(std::fmin(1.0, 0.5 * (double)hst[0].max_diam)) + 1e-6 : 0.0;
         if (margin > 0.3) margin = 0.3;
-        const double A = 0.25 * M_PI + margin;
-        double h = 0.75 * mean_src;
+        const double A = 0.25 * M_PI + margin;      // half-width of a face's domain as an angle
+        const double F = std::sin(A);               // ... and in face coordinates f = sin(angle)
+        double h = 0.75 * mean_src;                 // target bin size (radians)
         if (!(h > 2.0 * A / NB_CAP)) h = 2.0 * A / NB_CAP;
         if (hst[1].count == 0) h = 2.0 * A;
         int nb = (int)std::ceil(2.0 * A / h);
@@ -453,10 +454,10 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
         if (nb > NB_CAP) nb = NB_CAP;
         h = 2.0 * A / nb;
         P.nbx = P.nby = nb;
-        P.ox = P.oy = -A;
-        P.hx = P.hy = A;
-        P.inv_hq = BP_SUB / h;
-        P.eps = 1e-9;
+        P.ox = P.oy = -F;
+        P.hx = P.hy = F;
+        P.inv_hq = BP_SUB / (2.0 * F / nb);
+        P.eps = 1e-6;
         S.bin_size = h;
     } else {
         P.nfaces = 1;

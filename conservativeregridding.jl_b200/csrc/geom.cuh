@@ -67,12 +67,9 @@ __device__ __forceinline__ int cell_nverts(const CellsView &g, int64_t c, int64_
     return g.nv;
 }
 
-// signed area of cell c as stored (no orientation fix-up)
+// signed area of a ring as stored (no orientation fix-up)
 template <int DIM>
-__device__ double cell_signed_area(const CellsView &g, int64_t c) {
-    int64_t f;
-    const int n = cell_nverts<DIM>(g, c, &f);
-    const double *p = g.verts + f * DIM;
+__device__ double polygon_signed_area(const double *p, int n) {
     if (DIM == 3) {
         ExcessAcc acc;
         const d3 a = {p[0], p[1], p[2]};

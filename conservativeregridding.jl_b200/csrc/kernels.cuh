@@ -3,6 +3,7 @@
 #pragma once
 #include "common.cuh"
 #include "geom.cuh"
+#include "broadphase.cuh"
 
 namespace crg {
 
@@ -72,9 +73,12 @@ __global__ void __launch_bounds__(256) compact_pairs_kernel(const int2 *__restri
 template <int DIM>
 __global__ void __launch_bounds__(256) cell_area_kernel(CellsView g, double scale, double *__restrict__ areas,
                                                         uint8_t *__restrict__ flip, unsigned int *__restrict__ nflip) {
+    __shared__ CellStage<DIM> stage;
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int n;
+    const double *p = stage_cell<DIM>(g, c, &n, stage);
     if (c >= g.ncells) return;
-    const double a = cell_signed_area<DIM>(g, c);
+    const double a = polygon_signed_area<DIM>(p, n);
     areas[c] = fabs(a) * scale;
     const bool f = a < 0.0;
     flip[c] = f ? 1 : 0;

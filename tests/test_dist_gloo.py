@@ -21,6 +21,7 @@ class _OracleLocal:
         self.O = oracle.build_regridder(rows_grid, cols_grid)
         self.A = self.O.tocsc().tocsr()
         self.areas = torch.from_numpy(self.O.dst_areas.copy())
+        self.src_areas = torch.from_numpy(self.O.src_areas.copy())
         self.nnz = self.O.nnz
 
     def apply(self, out, x, normalize=True):
@@ -28,6 +29,9 @@ class _OracleLocal:
         if normalize:
             y = y / (self.O.dst_areas if y.ndim == 1 else self.O.dst_areas[:, None])
         out.copy_(torch.from_numpy(np.asarray(y)))
+
+    def apply_T(self, out, y_block):
+        out.copy_(torch.from_numpy(np.asarray(self.A.T @ y_block.numpy())))
 
 
 def _worker(rank, world, port, q):
@@ -49,12 +53,18 @@ def _worker(rank, world, port, q):
         y = S.regrid(x)                                   # broadcast from rank 0, all-gather
         x0 = np.random.default_rng(0).random(src.ncells)
         assert np.allclose(y.numpy(), full.regrid(x0), rtol=1e-13)
-        xb = S.regrid(y, transpose=True, broadcast=False)
+        xb = S.regrid(y, transpose=True)
         assert np.allclose(xb.numpy(), full.regrid(full.regrid(x0), transpose=True), rtol=1e-12)
         # batched (level-fastest) fields
         X = torch.from_numpy(np.stack([x0, 2 * x0, x0 ** 2], axis=1)) if rank == 0 else None
         Y = S.regrid(X, trailing=(3,))
         assert Y.shape == (dst.ncells, 3) and np.allclose(Y[:, 1].numpy(), 2 * full.regrid(x0), rtol=1e-13)
+        # transpose from the local block only, and un-normalised (A^T y)
+        lo, hi = block_bounds(dst.ncells, world)[rank]
+        xb2 = S.regrid(y[lo:hi].clone(), transpose=True) if world > 1 else xb
+        assert np.allclose(xb2.numpy(), xb.numpy(), rtol=1e-14)
+        xr = S.regrid(y, transpose=True, normalize=False)
+        assert np.allclose(xr.numpy(), full.tocsc().T @ y.numpy(), rtol=1e-12)
         # local block only
         lo, hi = block_bounds(dst.ncells, world)[rank]
         yl = S.regrid(torch.from_numpy(x0), broadcast=False, gather=False)
