@@ -352,7 +352,7 @@ def main():
             by_t = None
         apply_f_gbs = by_f / (fwd_ms * 1e-3) / 1e9 if world == 1 else None
         apply_t_gbs = by_t / (bwd_ms * 1e-3) / 1e9 if world == 1 else None
-        roof_clip = {"kernel": "clip_kernel<3,128,8>", "bound": "fp64", "achieved": clip_tflops, "peak": fp64_peak,
+        roof_clip = {"kernel": "clip_kernel<3,128,8,true>", "bound": "fp64", "achieved": clip_tflops, "peak": fp64_peak,
                      "unit": "TFLOP/s", "frac": clip_tflops / fp64_peak if fp64_peak else None, "traffic": None,
                      "peak_source": "crg_fp64_peak DFMA micro-benchmark, measured in this run",
                      "flops_per_pair": flops_per_pair, "pairs": n_cand, "ms": clip_ms,
@@ -499,11 +499,11 @@ def main():
         dist.destroy_process_group()
 
 
-# FP64 flops per candidate pair of clip_kernel<3,128,8> on the cfg5 workload, from the ncu capture
-# committed under profiles/ (DFMA counted as 2, DADD/DMUL as 1; see DESIGN.md section "Kernels").
-CLIP_FLOPS_PER_PAIR = 1.0
+# FP64 flops per candidate pair of clip_kernel<3,128,8,true> on the cfg5 workload, counted from the SASS page
+# of the ncu capture summarised in profiles/README.md (124.6 DFMA x 2 + 62.8 DMUL + 27.6 DADD per pair).
+CLIP_FLOPS_PER_PAIR = 339.6
 # dram__bytes_read.sum + dram__bytes_write.sum of one forward spmv launch on cfg5 (ncu --set full)
-SPMV_TRAFFIC_BYTES = None
+SPMV_TRAFFIC_BYTES = 161645824
 
 if __name__ == "__main__":
     main()
