@@ -198,8 +198,10 @@ __global__ void __launch_bounds__(256) spmm_lf_kernel(const int32_t *__restrict_
 
 // =======================================================================================
 // K8b: CSR SpMM, cell-fastest layout x[k * ldx + cell] (Julia dims = 1): one thread per row,
-// KC levels per thread so the row's (col, val) are read once per KC levels; output writes
-// are coalesced across rows.
+// KC levels per thread so the row's (col, val) are read once per KC levels; lanes hold
+// neighbouring rows, so a gather instruction touches few 128-byte lines, and output writes
+// are coalesced across rows.  (Measured alternatives on cfg3, K = 100: the same loop on the SELL
+// copy 249 us, row entries held in registers for a whole level group 212 us, this one 137 us.)
 // =======================================================================================
 template <int KC, bool DIVIDE>
 __global__ void __launch_bounds__(128) spmm_cf_kernel(const int32_t *__restrict__ rowptr,

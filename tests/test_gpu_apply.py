@@ -124,6 +124,16 @@ def test_long_rows_and_empty_rows(gpu):
     assert (y[np.diff(A.indptr) == 0] == 0).all()
     xb = np.zeros(src.ncells); regrid_(xb, transpose(R), np.ones(dst.ncells))
     assert np.allclose(xb, 1.0, atol=1e-9)
+    # batched, both layouts, through the cut (multi-piece) slices of the long rows
+    X = np.random.default_rng(5).random((src.ncells, 7))
+    ref = (A @ X) / R.dst_areas[:, None]
+    for order in ("C", "F"):
+        Y = np.full((dst.ncells, 7), np.nan, order=order)
+        regrid_(Y, R, np.asarray(X, order=order), dims=0)
+        assert np.allclose(Y, ref, rtol=1e-12, atol=0), order
+        Y2 = np.full((dst.ncells, 7), np.nan, order=order)
+        regrid_(Y2, R, np.asarray(X, order=order), dims=0, normalize=False)
+        assert np.allclose(Y2, A @ X, rtol=1e-12, atol=0), order
 
 
 @pytest.mark.parametrize("case", ["short", "long", "mixed", "empty_runs", "exact_chunks", "one_row"])
