@@ -288,8 +288,9 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
             if (nnz > 0) {
                 swap_key_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(ka, nnz, kb);      // kb = col<<32 | row
                 CRG_LAUNCH_CHECK();
-                split_csr_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(kb, (const double *)va, nnz, T.n_rows, T.rowptr.p,
-                                                                       T.colidx.p, T.vals.p);
+                split_csr_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(kb, (const double *)va, nnz, T.colidx.p, T.vals.p);
+            CRG_LAUNCH_CHECK();
+            rowptr_kernel<<<ceil_div(T.n_rows + 1, 256), 256, 0, st>>>(kb, nnz, T.n_rows, T.rowptr.p);
                 CRG_LAUNCH_CHECK();
             }
             CRG_TRY(finish_csr(T, st));
@@ -304,8 +305,9 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
         R->stats.sort_passes_csr = p2;
         CRG_TRY(alloc_csr(A, R->n_dst, R->n_src, nnz, st));
         if (nnz > 0) {
-            split_csr_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(ka, (const double *)va, nnz, A.n_rows, A.rowptr.p,
-                                                                   A.colidx.p, A.vals.p);
+            split_csr_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(ka, (const double *)va, nnz, A.colidx.p, A.vals.p);
+            CRG_LAUNCH_CHECK();
+            rowptr_kernel<<<ceil_div(A.n_rows + 1, 256), 256, 0, st>>>(ka, nnz, A.n_rows, A.rowptr.p);
             CRG_LAUNCH_CHECK();
         }
         CRG_TRY(finish_csr(A, st));
@@ -340,8 +342,9 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
     R->nnz = nnz;
     CRG_TRY(alloc_csr(A, R->n_dst, R->n_src, nnz, st));
     if (nnz > 0) {
-        split_csr_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(ka, (const double *)va, nnz, A.n_rows, A.rowptr.p,
-                                                               A.colidx.p, A.vals.p);
+        split_csr_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(ka, (const double *)va, nnz, A.colidx.p, A.vals.p);
+            CRG_LAUNCH_CHECK();
+            rowptr_kernel<<<ceil_div(A.n_rows + 1, 256), 256, 0, st>>>(ka, nnz, A.n_rows, A.rowptr.p);
         CRG_LAUNCH_CHECK();
     }
     CRG_TRY(finish_csr(A, st));
@@ -354,8 +357,9 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
             CRG_LAUNCH_CHECK();
             CRG_TRY(radix_sort_pairs(ka, va, kb, vb, nnz, 32, 32 + bits_src, &inb, &p3, st));
             if (inb) { std::swap(ka, kb); std::swap(va, vb); }
-            split_csr_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(ka, (const double *)va, nnz, T.n_rows, T.rowptr.p,
-                                                                   T.colidx.p, T.vals.p);
+            split_csr_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(ka, (const double *)va, nnz, T.colidx.p, T.vals.p);
+            CRG_LAUNCH_CHECK();
+            rowptr_kernel<<<ceil_div(T.n_rows + 1, 256), 256, 0, st>>>(ka, nnz, T.n_rows, T.rowptr.p);
             CRG_LAUNCH_CHECK();
         }
         CRG_TRY(finish_csr(T, st));

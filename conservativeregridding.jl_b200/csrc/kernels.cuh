@@ -113,21 +113,27 @@ __global__ void __launch_bounds__(256) swap_key_kernel(const uint64_t *__restric
     if (i < n) { const uint64_t k = in[i]; out[i] = (k << 32) | (k >> 32); }
 }
 
-// keys sorted by (row << 32 | col): write col indices, values and the row pointer array.
+// keys sorted by (row << 32 | col): write col indices and values ...
 __global__ void __launch_bounds__(256) split_csr_kernel(const uint64_t *__restrict__ keys,
                                                         const double *__restrict__ vals, int64_t nnz,
-                                                        int64_t n_rows, int32_t *__restrict__ rowptr,
                                                         int32_t *__restrict__ colidx, double *__restrict__ ovals) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nnz) return;
-    const uint64_t k = keys[i];
-    const int64_t r = (int64_t)(k >> 32);
-    colidx[i] = (int32_t)(uint32_t)k;
+    colidx[i] = (int32_t)(uint32_t)keys[i];
     ovals[i] = vals[i];
-    const int64_t rprev = i == 0 ? -1 : (int64_t)(keys[i - 1] >> 32);
-    for (int64_t rr = rprev + 1; rr <= r; ++rr) rowptr[rr] = (int32_t)i;
-    if (i == nnz - 1)
-        for (int64_t rr = r + 1; rr <= n_rows; ++rr) rowptr[rr] = (int32_t)nnz;
+}
+// ... and the row pointers: rowptr[r] = first entry whose row is >= r (binary search per row, so that
+// runs of empty rows -- half the rows of a destination-sharded transpose block -- cost nothing extra).
+__global__ void __launch_bounds__(256) rowptr_kernel(const uint64_t *__restrict__ keys, int64_t nnz, int64_t n_rows,
+                                                     int32_t *__restrict__ rowptr) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_rows) return;
+    int64_t lo = 0, hi = nnz;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)(keys[mid] >> 32) < r) lo = mid + 1; else hi = mid;
+    }
+    rowptr[r] = (int32_t)lo;
 }
 
 __global__ void __launch_bounds__(256) fill_i32_kernel(int32_t *p, int64_t n, int32_t v) {

@@ -48,13 +48,20 @@ class _LocalB200:
         self.nnz = self.R.intersections.nnz
         self.stats = self.R.intersections.stats()
 
-    @property
-    def areas(self):          # geometric areas of this rank's destination block
-        return torch.from_numpy(self.R.dst_areas)
+    def _areas(self, which: str, device):
+        n = self.R.shape[0] if which == "dst" else self.R.shape[1]
+        if device is not None and torch.device(device).type == "cuda":      # device to device, no host round trip
+            from .regridder import areas_to
+            t = torch.empty(n, dtype=torch.float64, device=device)
+            areas_to(self.R, **{f"{which}_areas_out": t})
+            return t
+        return torch.from_numpy(self.R.dst_areas if which == "dst" else self.R.src_areas)
 
-    @property
-    def src_areas(self):      # geometric areas of the (replicated) source grid
-        return torch.from_numpy(self.R.src_areas)
+    def areas(self, device=None):          # geometric areas of this rank's destination block
+        return self._areas("dst", device)
+
+    def src_areas(self, device=None):      # geometric areas of the (replicated) source grid
+        return self._areas("src", device)
 
     def apply(self, out: torch.Tensor, x: torch.Tensor, normalize: bool = True):
         """out = (A_r x) ./ a_dst_r"""
@@ -97,13 +104,13 @@ class ShardedRegridder:
     @property
     def dst_areas(self) -> torch.Tensor:
         if self._dst_areas is None:
-            self._dst_areas = self._all_gather_blocks(self.local.areas.to(self.device), self.dst_bounds)
+            self._dst_areas = self._all_gather_blocks(self.local.areas(self.device).to(self.device), self.dst_bounds)
         return self._dst_areas
 
     @property
     def src_areas(self) -> torch.Tensor:
         if self._src_areas is None:
-            self._src_areas = self.local.src_areas.to(self.device)
+            self._src_areas = self.local.src_areas(self.device).to(self.device)
         return self._src_areas
 
     @property

@@ -304,6 +304,15 @@ def _refresh_areas(R: RegridderB200):
     _lib.check(_lib.lib().crg_areas(M._h.ptr, da.ctypes.data, sa.ctypes.data))
 
 
+def areas_to(R: RegridderB200, dst_areas_out=None, src_areas_out=None):
+    """Copy ``R.dst_areas`` / ``R.src_areas`` into caller buffers (numpy arrays or CUDA tensors --
+    device to device, no host round trip).  For transpose(R) the roles are already swapped."""
+    M = R.intersections
+    d, s_ = (src_areas_out, dst_areas_out) if M.transposed else (dst_areas_out, src_areas_out)
+    _lib.check(_lib.lib().crg_areas(M._h.ptr, C.c_void_p(_ptr(d)) if d is not None else None,
+                                    C.c_void_p(_ptr(s_)) if s_ is not None else None))
+
+
 def normalize_(R: RegridderB200) -> RegridderB200:
     """``LinearAlgebra.normalize!(R)``: divide A and both area vectors by maximum(A)."""
     _lib.check(_lib.lib().crg_normalize(R.intersections._h.ptr))

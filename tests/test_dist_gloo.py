@@ -20,9 +20,13 @@ class _OracleLocal:
         from oracle import oracle
         self.O = oracle.build_regridder(rows_grid, cols_grid)
         self.A = self.O.tocsc().tocsr()
-        self.areas = torch.from_numpy(self.O.dst_areas.copy())
-        self.src_areas = torch.from_numpy(self.O.src_areas.copy())
         self.nnz = self.O.nnz
+
+    def areas(self, device=None):
+        return torch.from_numpy(self.O.dst_areas.copy())
+
+    def src_areas(self, device=None):
+        return torch.from_numpy(self.O.src_areas.copy())
 
     def apply(self, out, x, normalize=True):
         y = self.A @ x.numpy()
