@@ -760,9 +760,21 @@ static int apply_impl(crg_regridder *R, int transpose, int divide, double *dst, 
                 CRG_CUDA(cudaMemsetAsync(yd, 0, sizeof(double) * (size_t)n_out, st));
             } else {
                 const SellView V = M.sell_view();
-                const int nw = M.sell_nslices + M.sell_npieces;      // one warp per slice + extra pieces of cut slices
-                if (divide) spmv_sell_kernel<true><<<ceil_div(nw, 8), 256, 0, st>>>(V, xs, yd, areas);
-                else spmv_sell_kernel<false><<<ceil_div(nw, 8), 256, 0, st>>>(V, xs, yd, areas);
+                static const int mode = getenv("CRG_SELL_MODE") ? atoi(getenv("CRG_SELL_MODE")) : 0;
+                static const int bps = getenv("CRG_SELL_BPS") ? atoi(getenv("CRG_SELL_BPS")) : 8;
+                const double mean_steps = (double)M.sell_padded / 32.0 / (double)std::max(1, M.sell_nslices);
+                const bool pipelined = mode == 1 || (mode == 0 && mean_steps <= 6.0);
+                if (pipelined) {
+                    static int n_sm = 0;
+                    if (!n_sm) CRG_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, R->device));
+                    const int grid = std::min(ceil_div(M.sell_nslices, 8), bps * n_sm);
+                    if (divide) spmv_sell_pipelined_kernel<true><<<grid, 256, 0, st>>>(V, xs, yd, areas);
+                    else spmv_sell_pipelined_kernel<false><<<grid, 256, 0, st>>>(V, xs, yd, areas);
+                } else {
+                    const int nw = M.sell_nslices + M.sell_npieces;  // one warp per slice + extra pieces of cut slices
+                    if (divide) spmv_sell_kernel<true><<<ceil_div(nw, 8), 256, 0, st>>>(V, xs, yd, areas);
+                    else spmv_sell_kernel<false><<<ceil_div(nw, 8), 256, 0, st>>>(V, xs, yd, areas);
+                }
             }
         } else if (level_fastest) {
             const int nblk = ceil_div(n_out, 8);

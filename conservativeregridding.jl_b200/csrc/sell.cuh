@@ -181,4 +181,96 @@ __global__ void __launch_bounds__(256) spmv_sell_kernel(SellView S, const double
     sell_finish_cut<DIVIDE>(S, base, q, (steps + SELL_HP - 1) / SELL_HP, lane, r, acc, area, y);
 }
 
+
+// Persistent, software-pipelined variant: a warp walks slices s, s + W, s + 2W, ... and always has the
+// NEXT slice's header (offset, row length, permutation, area) and first SELL_UNR steps of (col, val) in
+// flight while it gathers x for the current one, so a slice costs about one memory latency instead of
+// three dependent ones.  Pays off when slices are short (transpose direction: ~3 entries per row).
+template <bool DIVIDE>
+__global__ void __launch_bounds__(256) spmv_sell_pipelined_kernel(SellView S, const double *__restrict__ x,
+                                                                  double *__restrict__ y,
+                                                                  const double *__restrict__ areas) {
+    const int lane = threadIdx.x & 31;
+    const int W = gridDim.x * (blockDim.x >> 5);
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    struct Hdr { int off, steps, len, r; };
+    auto load_hdr = [&](int s) {
+        Hdr h;
+        h.off = __ldg(&S.slice_off[s]);
+        h.steps = __ldg(&S.slice_off[s + 1]) - h.off;
+        h.len = __ldg(&S.rlen[(int64_t)s * 32 + lane]);
+        h.r = __ldg(&S.perm[(int64_t)s * 32 + lane]);
+        return h;
+    };
+    int c[SELL_UNR], cn[SELL_UNR];
+    double v[SELL_UNR], vn[SELL_UNR];
+    auto load_round = [&](const Hdr &h, int j, int (&cc)[SELL_UNR], double (&vv)[SELL_UNR]) {
+        const size_t e = ((size_t)h.off + j) * 32 + lane;
+        const int jend = min(h.len, SELL_HP);
+#pragma unroll
+        for (int u = 0; u < SELL_UNR; ++u) {
+            const bool ok = j + u < jend;
+            cc[u] = ok ? __ldg(S.cols + e + (size_t)u * 32) : 0;
+            vv[u] = ok ? __ldg(S.vals + e + (size_t)u * 32) : 0.0;
+        }
+    };
+    int s = w;
+    Hdr h{0, 0, 0, -1}, hn{0, 0, 0, -1};
+    double area = 1.0, arean = 1.0;
+    if (s < S.nslices) {
+        h = load_hdr(s);
+        load_round(h, 0, c, v);
+        if (DIVIDE && h.r >= 0) area = __ldg(&areas[h.r]);
+    }
+    while (s < S.nslices) {
+        const int sn = s + W;
+        if (sn < S.nslices) hn = load_hdr(sn);
+        // ---- current slice, round 0 is already in registers -------------------------------------------
+        const int jend = min(h.len, SELL_HP), wend = min(h.steps, SELL_HP);
+        double acc = 0.0;
+        {
+            double xv[SELL_UNR];
+#pragma unroll
+            for (int u = 0; u < SELL_UNR; ++u) xv[u] = (u < jend) ? __ldg(&x[c[u]]) : 0.0;
+            // the next slice's first round goes out before we wait for the gathers
+            if (sn < S.nslices) {
+                load_round(hn, 0, cn, vn);
+                if (DIVIDE && hn.r >= 0) arean = __ldg(&areas[hn.r]);
+            }
+#pragma unroll
+            for (int u = 0; u < SELL_UNR; ++u) if (u < jend) acc += v[u] * xv[u];
+        }
+        for (int j = SELL_UNR; j < wend; j += SELL_UNR) {      // taller slices: remaining rounds
+            int c2[SELL_UNR];
+            double v2[SELL_UNR];
+            load_round(h, j, c2, v2);
+#pragma unroll
+            for (int u = 0; u < SELL_UNR; ++u) if (j + u < jend) acc += v2[u] * __ldg(&x[c2[u]]);
+        }
+        if (h.steps <= SELL_HP) {
+            if (h.r >= 0) y[h.r] = DIVIDE ? acc / area : acc;
+        } else {                                               // piece 0 of a cut slice
+            sell_finish_cut<DIVIDE>(S, (int)__ldg(&S.cut_base[s]), 0, (h.steps + SELL_HP - 1) / SELL_HP, lane, h.r, acc,
+                                    area, y);
+        }
+        h = hn; area = arean; s = sn;
+#pragma unroll
+        for (int u = 0; u < SELL_UNR; ++u) { c[u] = cn[u]; v[u] = vn[u]; }
+    }
+    // ---- extra pieces of cut slices (rare) -----------------------------------------------------------------
+    for (int p = w; p < S.npieces; p += W) {
+        const int4 d = __ldg(&S.pieces[p]);
+        const Hdr hp = load_hdr(d.x);
+        const int jend = min(hp.len, d.y + SELL_HP), wend = min(hp.steps, d.y + SELL_HP);
+        const double *vp = S.vals + ((size_t)hp.off + d.y) * 32 + lane;
+        const int32_t *cp = S.cols + ((size_t)hp.off + d.y) * 32 + lane;
+        double acc = 0.0;
+        for (int j = d.y; j < wend; ++j, vp += 32, cp += 32)
+            if (j < jend) acc += __ldg(vp) * __ldg(&x[__ldg(cp)]);
+        double ar = 1.0;
+        if (DIVIDE && hp.r >= 0) ar = __ldg(&areas[hp.r]);
+        sell_finish_cut<DIVIDE>(S, d.z, d.w & 0xffff, d.w >> 16, lane, hp.r, acc, ar, y);
+    }
+}
+
 }  // namespace crg
