@@ -45,15 +45,16 @@ mutable struct B200Matrix <: AbstractMatrix{Float64}
     n_dst::Int
     n_src::Int
     transposed::Bool
-    owner::Bool
+    owner::Union{Nothing, B200Matrix}   # transposed views keep the owning matrix (and its handle) alive
     function B200Matrix(h, n_dst, n_src, transposed, owner)
         A = new(h, n_dst, n_src, transposed, owner)
-        owner && finalizer(a -> ccall((:crg_free, lib), Cint, (Ptr{Cvoid},), a.h), A)
+        owner === nothing && finalizer(a -> ccall((:crg_free, lib), Cint, (Ptr{Cvoid},), a.h), A)
         return A
     end
 end
 Base.size(A::B200Matrix) = A.transposed ? (A.n_src, A.n_dst) : (A.n_dst, A.n_src)
-LinearAlgebra.transpose(A::B200Matrix) = B200Matrix(A.h, A.n_dst, A.n_src, !A.transposed, false)
+LinearAlgebra.transpose(A::B200Matrix) =
+    B200Matrix(A.h, A.n_dst, A.n_src, !A.transposed, A.owner === nothing ? A : A.owner)
 Base.getindex(A::B200Matrix, i::Int, j::Int) = SparseArrays.sparse(A)[i, j]   # slow; tests only
 
 function SparseArrays.sparse(A::B200Matrix)
@@ -145,8 +146,36 @@ function b200_regridder(manifold::GOCore.Manifold, dst, src; normalize = false, 
     n_dst, n_src = length(doff) - 1, length(soff) - 1
     dst_areas = Vector{Float64}(undef, n_dst); src_areas = Vector{Float64}(undef, n_src)
     check(ccall((:crg_areas, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), h[], dst_areas, src_areas))
-    A = B200Matrix(h[], n_dst, n_src, false, true)
+    A = B200Matrix(h[], n_dst, n_src, false, nothing)
     return Regridder(A, dst_areas, src_areas, zeros(n_dst), zeros(n_src))
+end
+
+# ---- described grids: no vertex soup, cells are generated on the device (crg_build_grids) --------------
+struct CrgGrid               # mirrors crg_grid
+    kind::Int32
+    flags::Int32
+    cells::CrgCells
+    n1::Int64
+    n2::Int64
+    p::NTuple{4, Float64}
+    lat_deg::Ptr{Float64}
+end
+const NOCELLS = CrgCells(C_NULL, C_NULL, 0, 0, 0)
+"HealpixMap -> descriptor (ext/ConservativeRegriddingHealpixExt.jl:18): nside + ordering."
+healpix_grid(nside::Integer; nested::Bool = false) = CrgGrid(2, nested ? 1 : 0, NOCELLS, nside, 0, (0.0, 0.0, 0.0, 0.0), C_NULL)
+"Oceananigans LatitudeLongitudeGrid -> descriptor (ext/ConservativeRegriddingOceananigansExt.jl:242-264)."
+lonlat_grid(nlon, nlat; longitude = (0.0, 360.0), latitude = (-90.0, 90.0)) =
+    CrgGrid(1, 0, NOCELLS, nlon, nlat, (longitude[1], longitude[2], latitude[1], latitude[2]), C_NULL)
+
+function b200_regridder(dst::CrgGrid, src::CrgGrid; radius = 1.0, normalize = false, device = -1)
+    opts = CrgOptions(1, normalize, radius, 0.0, device, 1, 0, 0, C_NULL)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:crg_build_grids, lib), Cint, (Ref{CrgOptions}, Ref{CrgGrid}, Ref{CrgGrid}, Ptr{Ptr{Cvoid}}), opts, dst, src, h))
+    n_dst = Ref{Int64}(0); n_src = Ref{Int64}(0)
+    check(ccall((:crg_dims, lib), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}), h[], n_dst, n_src, C_NULL))
+    dst_areas = Vector{Float64}(undef, n_dst[]); src_areas = Vector{Float64}(undef, n_src[])
+    check(ccall((:crg_areas, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), h[], dst_areas, src_areas))
+    return Regridder(B200Matrix(h[], n_dst[], n_src[], false, nothing), dst_areas, src_areas, zeros(n_dst[]), zeros(n_src[]))
 end
 
 end # module
