@@ -772,8 +772,9 @@ static int apply_impl(crg_regridder *R, int transpose, int divide, double *dst, 
                     else spmv_sell_pipelined_kernel<false><<<grid, 256, 0, st>>>(V, xs, yd, areas);
                 } else {
                     const int nw = M.sell_nslices + M.sell_npieces;  // one warp per slice + extra pieces of cut slices
-                    if (divide) spmv_sell_kernel<true><<<ceil_div(nw, 8), 256, 0, st>>>(V, xs, yd, areas);
-                    else spmv_sell_kernel<false><<<ceil_div(nw, 8), 256, 0, st>>>(V, xs, yd, areas);
+                    constexpr int BS = 128;                          // measured: 128 > 256 threads, 4 steps in flight > 2, 6, 8
+                    if (divide) spmv_sell_kernel<true, SELL_UNR><<<ceil_div(nw, BS / 32), BS, 0, st>>>(V, xs, yd, areas);
+                    else spmv_sell_kernel<false, SELL_UNR><<<ceil_div(nw, BS / 32), BS, 0, st>>>(V, xs, yd, areas);
                 }
             }
         } else if (level_fastest) {

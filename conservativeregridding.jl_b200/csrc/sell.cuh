@@ -25,6 +25,9 @@ namespace crg {
 constexpr int SELL_SIGMA = 1024;   // sorting window (rows)
 constexpr int SELL_HP = 32;        // max steps per piece
 constexpr int SELL_UNR = 4;
+#ifndef SELL_LD
+#define SELL_LD __ldcs
+#endif
 
 struct SellView {
     const double *vals;        // padded, slice-major
@@ -133,7 +136,7 @@ __device__ __forceinline__ void sell_finish_cut(const SellView &S, int base, int
 
 // One warp per slice (lane = row), SELL_UNR steps in flight at once.  Warps beyond the slice range run
 // the extra pieces of cut slices.
-template <bool DIVIDE>
+template <bool DIVIDE, int UNR>
 __global__ void __launch_bounds__(256) spmv_sell_kernel(SellView S, const double *__restrict__ x, double *__restrict__ y,
                                                         const double *__restrict__ areas) {
     const int lane = threadIdx.x & 31;
@@ -158,20 +161,20 @@ __global__ void __launch_bounds__(256) spmv_sell_kernel(SellView S, const double
     const double *vp = S.vals + ((size_t)off + j0) * 32 + lane;
     const int32_t *cp = S.cols + ((size_t)off + j0) * 32 + lane;
     double acc = 0.0;
-    for (int j = j0; j < wend; j += SELL_UNR) {
-        int c[SELL_UNR];
-        double v[SELL_UNR], xv[SELL_UNR];
+    for (int j = j0; j < wend; j += UNR) {
+        int c[UNR];
+        double v[UNR], xv[UNR];
 #pragma unroll
-        for (int u = 0; u < SELL_UNR; ++u) {
+        for (int u = 0; u < UNR; ++u) {
             const bool ok = j + u < jend;
-            c[u] = ok ? __ldg(cp + (size_t)u * 32) : 0;
-            v[u] = ok ? __ldg(vp + (size_t)u * 32) : 0.0;
+            c[u] = ok ? SELL_LD(cp + (size_t)u * 32) : 0;      // matrix stream: read once, evict first
+            v[u] = ok ? SELL_LD(vp + (size_t)u * 32) : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < SELL_UNR; ++u) xv[u] = (j + u < jend) ? __ldg(&x[c[u]]) : 0.0;
+        for (int u = 0; u < UNR; ++u) xv[u] = (j + u < jend) ? __ldg(&x[c[u]]) : 0.0;
 #pragma unroll
-        for (int u = 0; u < SELL_UNR; ++u) if (j + u < jend) acc += v[u] * xv[u];
-        vp += SELL_UNR * 32; cp += SELL_UNR * 32;
+        for (int u = 0; u < UNR; ++u) if (j + u < jend) acc += v[u] * xv[u];
+        vp += UNR * 32; cp += UNR * 32;
     }
     if (steps <= SELL_HP) {                             // the whole slice is this piece
         if (r >= 0) y[r] = DIVIDE ? acc / area : acc;
@@ -210,8 +213,8 @@ __global__ void __launch_bounds__(256) spmv_sell_pipelined_kernel(SellView S, co
 #pragma unroll
         for (int u = 0; u < SELL_UNR; ++u) {
             const bool ok = j + u < jend;
-            cc[u] = ok ? __ldg(S.cols + e + (size_t)u * 32) : 0;
-            vv[u] = ok ? __ldg(S.vals + e + (size_t)u * 32) : 0.0;
+            cc[u] = ok ? SELL_LD(S.cols + e + (size_t)u * 32) : 0;
+            vv[u] = ok ? SELL_LD(S.vals + e + (size_t)u * 32) : 0.0;
         }
     };
     int s = w;
