@@ -298,3 +298,56 @@ def test_described_grids_build_the_same_regridder(gpu):
     assert abs(R4.intersections.tocsc() - Regridder(ds, ss).intersections.tocsc()).max() == 0.0
     with pytest.raises(_lib.CrgError):
         Regridder(grids.GridSpec("healpix", 12), ss)        # nside not a power of two
+
+
+def _rotation(rng):
+    q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    if np.linalg.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    return q
+
+
+def test_rotated_polar_and_identical_grids(gpu):
+    """Geometry the structured tests do not reach: arbitrarily rotated grids (no cell edge follows a
+    coordinate line, the poles fall inside ordinary cells), ragged cells that CONTAIN a pole, and a grid
+    regridded onto itself (every edge coincident)."""
+    oracle = _oracle()
+    rng = np.random.default_rng(42)
+    # rotated HEALPix <- rotated lon-lat
+    Q1, Q2 = _rotation(rng), _rotation(rng)
+    dst = grids.Grid(np.ascontiguousarray(grids.healpix_grid(16, "ring").verts @ Q1.T), grids.SPHERICAL)
+    src = grids.Grid(np.ascontiguousarray(grids.lonlat_grid(72, 36).verts @ Q2.T), grids.SPHERICAL)
+    R = Regridder(dst, src)
+    O = oracle.build_regridder(dst, src, nthreads=oracle.max_threads())
+    compare_matrices(R.intersections.tocsc(), O.tocsc(), O.dst_areas, O.src_areas)
+    A = R.intersections.tocsr()
+    assert np.allclose(np.asarray(A.sum(1)).ravel(), R.dst_areas, rtol=1.5e-8)
+    assert np.allclose(np.asarray(A.sum(0)).ravel(), R.src_areas, rtol=1.5e-8)
+    # polar caps as octagons that contain the pole + bands of quads (ragged: offsets path)
+    def cap_grid(nlon, lats):
+        polys = []
+        lon = np.arange(nlon) * 360.0 / nlon
+        polys.append(grids.unit_sphere_from_geographic(lon, np.full(nlon, lats[-1]))[::1])          # north cap, CCW
+        polys.append(grids.unit_sphere_from_geographic(lon[::-1], np.full(nlon, lats[0])))          # south cap, CCW from outside
+        for j in range(len(lats) - 1):
+            for i in range(nlon):
+                lo, hi = lon[i], lon[i] + 360.0 / nlon
+                polys.append(grids.unit_sphere_from_geographic(np.array([lo, hi, hi, lo]),
+                                                               np.array([lats[j], lats[j], lats[j + 1], lats[j + 1]])))
+        return grids.polygons_grid(polys, grids.SPHERICAL)
+    gc = cap_grid(8, np.array([-60.0, -20.0, 20.0, 60.0]))
+    assert gc.offsets is not None
+    gs = grids.healpix_grid(4, "nested")
+    R = Regridder(gc, gs)
+    O = oracle.build_regridder(gc, gs)
+    compare_matrices(R.intersections.tocsc(), O.tocsc(), O.dst_areas, O.src_areas)
+    assert abs(R.dst_areas.sum() / (4 * np.pi) - 1) < 1e-12          # caps + bands tile the sphere
+    y = np.zeros(gc.ncells); regrid_(y, R, np.ones(gs.ncells))
+    assert np.allclose(y, 1.0, atol=1e-10)
+    # a grid onto itself: the matrix is diag(areas) up to round-off slivers
+    g = grids.healpix_grid(8, "ring")
+    R = Regridder(g, g)
+    A = R.intersections.tocsr()
+    assert np.allclose(A.diagonal(), R.dst_areas, rtol=1e-12)
+    off = A - sp.diags(A.diagonal())
+    assert off.nnz == 0 or abs(off).max() < 1e-12 * R.dst_areas.max()
