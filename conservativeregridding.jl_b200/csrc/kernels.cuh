@@ -207,9 +207,11 @@ __global__ void __launch_bounds__(256) spmm_lf_kernel(const int32_t *__restrict_
 // KC levels per thread so the row's (col, val) are read once per KC levels; lanes hold
 // neighbouring rows, so a gather instruction touches few 128-byte lines, and output writes
 // are coalesced across rows.  (Measured alternatives on cfg3, K = 100: the same loop on the SELL
-// copy 249 us, row entries held in registers for a whole level group 212 us, this one 137 us.)
+// copy 249 us, row entries held in registers for a whole level group 212 us, one entry per
+// iteration 137 us, U = 2 entries per iteration 112 us, U = 4 109-121 us at 122 registers.  ncu: L1
+// wavefronts bound it -- the j-th entries of 32 neighbouring rows lie on ~13 different lines.)
 // =======================================================================================
-template <int KC, bool DIVIDE>
+template <int KC, bool DIVIDE, int U = 2>
 __global__ void __launch_bounds__(128) spmm_cf_kernel(const int32_t *__restrict__ rowptr,
                                                       const int32_t *__restrict__ colidx,
                                                       const double *__restrict__ vals, const double *__restrict__ x,
@@ -222,14 +224,28 @@ __global__ void __launch_bounds__(128) spmm_cf_kernel(const int32_t *__restrict_
     double acc[KC];
 #pragma unroll
     for (int t = 0; t < KC; ++t) acc[t] = 0.0;
-    for (int j = a; j < b; ++j) {
-        const double v = vals[j];
-        const double *xp = x + colidx[j] + k0 * ldx;
-#pragma unroll
-        for (int t = 0; t < KC; ++t)
-            if (k0 + t < K) acc[t] += v * __ldg(&xp[t * ldx]);
-    }
     const double ar = DIVIDE ? areas[r] : 1.0;
+    // U entries per iteration, all U*KC gathers issued before the first FMA (memory-level
+    // parallelism); entries past the row end are clamped to the last one with weight 0.
+    for (int j = a; j < b; j += U) {
+        double v[U];
+        const double *xp[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int jj = min(j + u, b - 1);
+            v[u] = j + u < b ? vals[jj] : 0.0;
+            xp[u] = x + colidx[jj] + k0 * ldx;
+        }
+        double g[U][KC];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int t = 0; t < KC; ++t) g[u][t] = k0 + t < K ? __ldg(&xp[u][t * ldx]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int t = 0; t < KC; ++t) acc[t] += v[u] * g[u][t];
+    }
 #pragma unroll
     for (int t = 0; t < KC; ++t)
         if (k0 + t < K) y[(k0 + t) * ldy + r] = DIVIDE ? acc[t] / ar : acc[t];

@@ -67,7 +67,7 @@ def test_nd_arrays_and_dims(gpu):
     assert np.allclose(d2, A @ s2, rtol=1e-14)
 
 
-@pytest.mark.parametrize("K", [1, 3, 32, 33, 100])
+@pytest.mark.parametrize("K", [1, 3, 18, 32, 33, 64, 100, 130, 200])
 def test_batched_spmm_matches_loop_of_spmv(gpu, K):
     """BASELINE config 3 shape (cubed sphere -> lon-lat, K levels) at reduced size: one SpMM launch
     == K SpMVs (regrid.jl:303-318), both memory layouts, forward and transpose."""
