@@ -28,6 +28,7 @@ constexpr int BP_SUB = 16;              // quantisation: sub-bins per bin
 constexpr int BP_MAX_BINS_1D = 4095;    // so that quantised coordinates fit 16 bits
 constexpr int BP_MAX_COVER = 4096;      // a source cell covering more bins is "big"
 constexpr int BP_MAX_QUERY = 1 << 18;   // a destination cell covering more bins is "big"
+constexpr int BP_SHORT_ROW = 48;        // rows with at most this many candidates are column-sorted by one thread
 constexpr double BP_BIG_ANGLE = 0.2;    // rad; larger spherical cells are "big"
 constexpr double BP_MIN_W = 0.05;       // a face is usable only if all vertices have w > this
 
@@ -268,7 +269,8 @@ __device__ __forceinline__ int home_face(const double *p, int n) {
 }
 
 // FILL = false: cand_count[d] = number of candidates of destination cell d; big destination
-//               cells (count = n_src) are appended to big_dst.
+//               cells (count = n_src) are appended to big_dst; big_dst_counter[1] is set when some
+//               cell has more than BP_SHORT_ROW candidates.
 // FILL = true : pairs[cand_off[d] + k] = (src, d); big destination cells are skipped (filled by
 //               bp_fill_big_dst_kernel).
 template <int DIM, bool FILL>
@@ -302,6 +304,7 @@ __global__ void __launch_bounds__(128) bp_query_kernel(CellsView g, const float 
         if (!FILL) {
             cand_count[d] = (uint32_t)n_src;
             big_dst[atomicAdd(big_dst_counter, 1u)] = (int32_t)d;
+            if (n_src > BP_SHORT_ROW) big_dst_counter[1] = 1u;
         }
         return;
     }
@@ -326,7 +329,10 @@ __global__ void __launch_bounds__(128) bp_query_kernel(CellsView g, const float 
         if (FILL) out[cnt] = make_int2(big_src[k], (int)d);
         ++cnt;
     }
-    if (!FILL) cand_count[d] = cnt;
+    if (!FILL) {
+        cand_count[d] = cnt;
+        if (cnt > BP_SHORT_ROW) big_dst_counter[1] = 1u;      // flag: some row is long (benign race, same value)
+    }
 }
 
 __global__ void __launch_bounds__(256) bp_fill_big_dst_kernel(const int32_t *__restrict__ big_dst,

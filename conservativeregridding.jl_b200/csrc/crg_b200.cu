@@ -258,7 +258,7 @@ static int finish_csr(Csr &M, cudaStream_t st) { return build_sell(M, st); }
 //   row_sorted_unique = false (crg_build_from_coo: arbitrary order, duplicates): full-key sort,
 //     segmented duplicate sum, then the column-bit passes for the transpose.
 static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &valA, int64_t n, bool row_sorted_unique,
-                    Timer &tm, int *t_sort_csr0, int *t_sort_csr1, int *t_sort_csc1) {
+                    bool short_rows, Timer &tm, int *t_sort_csr0, int *t_sort_csr1, int *t_sort_csc1) {
     cudaStream_t st = R->stream;
     const int bits_src = ilog2_ceil((uint64_t)(R->n_src > 1 ? R->n_src : 2));
     const int bits_dst = ilog2_ceil((uint64_t)(R->n_dst > 1 ? R->n_dst : 2));
@@ -277,6 +277,42 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
     Csr &T = R->At;
     R->has_At = false;
     if (n >= ((int64_t)1 << 31)) return set_error(CRG_ERR_NOMEM, "nnz=%lld exceeds int32 indexing", (long long)n);
+
+    if (row_sorted_unique && short_rows) {
+        // every row is a few entries long: CSR(A) straight from the row-grouped triples (one thread
+        // sorts a row by column), then the column-bit passes alone give the (col, row) order.
+        R->nnz = nnz;
+        CRG_TRY(alloc_csr(A, R->n_dst, R->n_src, nnz, st));
+        if (nnz > 0) {
+            rowptr_kernel<<<ceil_div(A.n_rows + 1, 256), 256, 0, st>>>(ka, nnz, A.n_rows, A.rowptr.p);
+            CRG_LAUNCH_CHECK();
+            row_sort_split_kernel<<<ceil_div(A.n_rows, ROWSORT_ROWS), ROWSORT_ROWS, 0, st>>>(ka, (double *)va, A.rowptr.p, A.n_rows, A.colidx.p, A.vals.p);
+            CRG_LAUNCH_CHECK();
+        }
+        CRG_TRY(finish_csr(A, st));
+        R->stats.sort_passes_csr = 0;
+        *t_sort_csr1 = (int)tm.ev.size();
+        CRG_TRY(tm.mark());
+        if (R->opts.build_transpose) {
+            CRG_TRY(radix_sort_pairs(ka, va, kb, vb, n, 0, bits_src, &inb, &p1, st));
+            if (inb) { std::swap(ka, kb); std::swap(va, vb); }
+            CRG_TRY(alloc_csr(T, R->n_src, R->n_dst, nnz, st));
+            if (nnz > 0) {
+                swap_key_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(ka, nnz, kb);      // kb = col<<32 | row
+                CRG_LAUNCH_CHECK();
+                split_csr_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(kb, (const double *)va, nnz, T.colidx.p, T.vals.p);
+                CRG_LAUNCH_CHECK();
+                rowptr_kernel<<<ceil_div(T.n_rows + 1, 256), 256, 0, st>>>(kb, nnz, T.n_rows, T.rowptr.p);
+                CRG_LAUNCH_CHECK();
+            }
+            CRG_TRY(finish_csr(T, st));
+            R->has_At = true;
+        }
+        R->stats.sort_passes_csc = p1;
+        *t_sort_csc1 = (int)tm.ev.size();
+        CRG_TRY(tm.mark());
+        return CRG_OK;
+    }
 
     if (row_sorted_unique) {
         R->nnz = nnz;
@@ -537,6 +573,8 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     CRG_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, st));
     CRG_CUDA(cudaStreamSynchronize(st));
     const int n_big_dst = (int)h_counters[1];
+    static const bool allow_rowsort = !(getenv("CRG_ROW_SORT") && atoi(getenv("CRG_ROW_SORT")) == 0);
+    const bool short_rows = allow_rowsort && h_counters[2] == 0;   // no destination cell has more than BP_SHORT_ROW candidates
     S.n_candidates = n_cand;
     S.n_big_dst = n_big_dst;
     if (n_cand >= ((int64_t)1 << 32))
@@ -607,7 +645,7 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
 
     // ---- K5: assembly ------------------------------------------------------------------------------
     int t0 = 0, t1 = 0, t2 = 0;
-    CRG_TRY(assemble(R, coo_key, coo_val, (int64_t)h_keep, true, tm, &t0, &t1, &t2));
+    CRG_TRY(assemble(R, coo_key, coo_val, (int64_t)h_keep, true, short_rows, tm, &t0, &t1, &t2));
     coo_key.release(); coo_val.release();
 
     // ---- K6: normalize ------------------------------------------------------------------------------
@@ -1060,7 +1098,7 @@ int crg_build_from_coo(const crg_options *opts, int64_t n_dst, int64_t n_src, in
         else CRG_CUDA(cudaMemsetAsync(R->src_areas.p, 0, sizeof(double) * (size_t)(n_src > 0 ? n_src : 1), st));
         CRG_TRY(tm.mark());
         int a = 0, b = 0, c = 0;
-        CRG_TRY(assemble(R, keys, vals, nnz, false, tm, &a, &b, &c));
+        CRG_TRY(assemble(R, keys, vals, nnz, false, false, tm, &a, &b, &c));
         if (R->opts.normalize) CRG_TRY(do_normalize(R));
         CRG_TRY(tm.mark());
         CRG_CUDA(cudaStreamSynchronize(st));

@@ -136,6 +136,59 @@ __global__ void __launch_bounds__(256) rowptr_kernel(const uint64_t *__restrict_
     rowptr[r] = (int32_t)lo;
 }
 
+// Row-grouped COO with short rows -> CSR: a block stages the entries of its ROWSORT_ROWS rows in
+// shared memory (coalesced), one thread per row sorts its entries by column (insertion sort; the
+// candidate lists are a few entries long), and the block writes the CSR column/value arrays and the
+// (row, col)-ordered triples (input of the column passes of the transpose) back, coalesced.
+// A block whose rows hold more than ROWSORT_CAP entries sorts in place in global memory.
+constexpr int ROWSORT_ROWS = 128;
+constexpr int ROWSORT_CAP = 2560;
+__global__ void __launch_bounds__(ROWSORT_ROWS) row_sort_split_kernel(uint64_t *__restrict__ keys, double *__restrict__ vals,
+                                                                      const int32_t *__restrict__ rowptr, int64_t n_rows,
+                                                                      int32_t *__restrict__ colidx,
+                                                                      double *__restrict__ out_vals) {
+    __shared__ uint64_t sk[ROWSORT_CAP];
+    __shared__ double sv[ROWSORT_CAP];
+    const int64_t r0 = (int64_t)blockIdx.x * ROWSORT_ROWS;
+    const int64_t r = r0 + threadIdx.x;
+    const int64_t r1 = min(r0 + (int64_t)ROWSORT_ROWS, n_rows);
+    const int A = rowptr[r0], B = rowptr[r1];
+    const bool staged = B - A <= ROWSORT_CAP;                                // block-uniform
+    uint64_t *k_ = staged ? sk - A : keys;                                   // indexed by the global entry number
+    double *v_ = staged ? sv - A : vals;
+    if (staged) {
+        for (int i = A + threadIdx.x; i < B; i += ROWSORT_ROWS) { sk[i - A] = keys[i]; sv[i - A] = vals[i]; }
+        __syncthreads();
+    }
+    if (r < n_rows) {
+        const int a = rowptr[r], b = rowptr[r + 1];
+        for (int i = a + 1; i < b; ++i) {
+            const uint64_t k = k_[i];
+            const double v = v_[i];
+            int j = i - 1;
+            while (j >= a) {
+                const uint64_t kj = k_[j];
+                if (kj <= k) break;
+                k_[j + 1] = kj;
+                v_[j + 1] = v_[j];
+                --j;
+            }
+            if (j + 1 != i) { k_[j + 1] = k; v_[j + 1] = v; }
+        }
+        if (!staged)
+            for (int j = a; j < b; ++j) { colidx[j] = (int32_t)(uint32_t)keys[j]; out_vals[j] = vals[j]; }
+    }
+    if (staged) {
+        __syncthreads();
+        for (int i = A + threadIdx.x; i < B; i += ROWSORT_ROWS) {
+            const uint64_t k = sk[i - A];
+            const double v = sv[i - A];
+            keys[i] = k; vals[i] = v;
+            colidx[i] = (int32_t)(uint32_t)k; out_vals[i] = v;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) fill_i32_kernel(int32_t *p, int64_t n, int32_t v) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
