@@ -228,26 +228,59 @@ __device__ __forceinline__ void load_quad(const double *__restrict__ p, bool fli
         for (int k = 0; k < DIM; ++k) v[i][k] = flip ? t[(3 - i) * DIM + k] : t[i * DIM + k];
 }
 
+// One edge (p -> q) of the subject polygon that crosses the clip line, with the signed distances
+// (dp, dq) of its ends.  point(): where it crosses.
+//   planar : p + t (q - p), t = dp / (dp - dq)                       (Sutherland-Hodgman)
+//   sphere : the same chord point pushed back to the unit sphere.  (dp - dq) (p + t (q - p)) =
+//            dp q - dq p, so the direction needs no division: normalise sign(dp - dq) (dp q - dq p).
+//            (Differs from "divide, interpolate, normalise" by rounding only, ~1e-16 relative.)
+constexpr double CLIP_SNAP = 4e-15;   // relative position along the edge below which a crossing is an end vertex
+
+template <int DIM>
+struct Crossing {
+    double px = 1.0, py = 0.0, pz = 0.0, qx = 0.0, qy = 1.0, qz = 0.0, dp = 1.0, dq = -1.0;
+    __device__ __forceinline__ void point(double &rx, double &ry, double &rz) const {
+        if (DIM == 3) {
+            rx = fma(dp, qx, -(dq * px));
+            ry = fma(dp, qy, -(dq * py));
+            rz = fma(dp, qz, -(dq * pz));
+            double inv = rsqrt(fma(rx, rx, fma(ry, ry, rz * rz)));
+            if (dp < dq) inv = -inv;
+            rx *= inv; ry *= inv; rz *= inv;
+        } else {
+            const double t = dp / (dp - dq);
+            rx = fma(t, qx - px, px); ry = fma(t, qy - py, py); rz = 0.0;
+        }
+    }
+};
+
 template <int DIM, int NT>
 __device__ double clip_quad_area(const CellsView &gs, int64_t s, const CellsView &gc, int64_t c,
                                  double *smem /* 8 * DIM * NT doubles */) {
     constexpr int MAXW = 8;
     PolyBuf<DIM, NT, MAXW> cur{smem + threadIdx.x};
-    double cv[4][DIM];
     {
         double sv[4][DIM];
         load_quad<DIM>(gs.verts + s * 4 * DIM, gs.flip && gs.flip[s], sv);
-        load_quad<DIM>(gc.verts + c * 4 * DIM, gc.flip && gc.flip[c], cv);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int k = 0; k < DIM; ++k) cur.set(i, k, sv[i][k]);
     }
+    // The clip cell is NOT kept in registers (24 of them): each pass fetches the one new end of its
+    // edge (an L1 hit -- consecutive pairs share the destination cell) and keeps the other.
+    const double *cbase = gc.verts + c * 4 * DIM;
+    const bool cflip = gc.flip && gc.flip[c];
+    double u[3], v[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) v[k] = __ldg(cbase + (cflip ? 3 : 0) * DIM + k);
     int m = 4;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         if (m == 0) break;
-        const double *u = cv[e], *v = cv[(e + 1) & 3];
+        const int vi = (e + 1) & 3;
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) { u[k] = v[k]; v[k] = __ldg(cbase + (cflip ? 3 - vi : vi) * DIM + k); }
         double nx, ny, nz = 0.0, h0 = 0.0;
         if (DIM == 3) {
             nx = u[1] * v[2] - u[2] * v[1]; ny = u[2] * v[0] - u[0] * v[2]; nz = u[0] * v[1] - u[1] * v[0];
@@ -273,14 +306,23 @@ __device__ double clip_quad_area(const CellsView &gs, int64_t s, const CellsView
             else { q2x = Lx; q2y = Ly; q2z = Lz; }
             const double dq = DIM == 3 ? fma(nx, qx, fma(ny, qy, nz * qz)) : fma(nx, qx, fma(ny, qy, h0));
             const bool in_p = dp >= 0.0, in_q = dq >= 0.0;
-            if (in_p != in_q) {
-                const double t = dp / (dp - dq);
-                double rx = fma(t, qx - px, px), ry = fma(t, qy - py, py), rz = fma(t, qz - pz, pz);
-                if (DIM == 3) {
-                    const double inv = rsqrt(rx * rx + ry * ry + rz * rz);
-                    rx *= inv; ry *= inv; rz *= inv;
+            if (in_p != in_q && mo <= i + 2 && mo < MAXW) {
+                // A crossing within CLIP_SNAP of an end of the edge IS that vertex: reuse its exact
+                // coordinates (or emit nothing when the vertex is emitted anyway) instead of a
+                // rounded near-duplicate.  On coincident edges (identical or nested grids) the
+                // distances are rounding noise; near-duplicates there classify inconsistently in
+                // the later passes and the vertex count outgrows the in-place buffer.
+                const double adp = fabs(dp), adq = fabs(dq);
+                double rx = qx, ry = qy, rz = qz;
+                bool emit = true;
+                if (adq <= CLIP_SNAP * adp) emit = !in_q;                      // at q (q inside: emitted below)
+                else if (adp <= CLIP_SNAP * adq) { emit = !in_p; rx = px; ry = py; rz = pz; }   // at p
+                else {
+                    Crossing<DIM> c;
+                    c.px = px; c.py = py; c.pz = pz; c.qx = qx; c.qy = qy; c.qz = qz; c.dp = dp; c.dq = dq;
+                    c.point(rx, ry, rz);
                 }
-                if (mo <= i + 2 && mo < MAXW) {
+                if (emit) {
                     cur.set(mo, 0, rx); cur.set(mo, 1, ry);
                     if (DIM == 3) cur.set(mo, 2, rz);
                     ++mo;

@@ -72,3 +72,26 @@ def test_analytic_fields_are_conserved(gpu, field):
     # round trip back to the source grid stays close (oceananigans.jl:15-35: rtol 1e-5 on the mean)
     xb = np.zeros(src.ncells); regrid_(xb, transpose(R), y)
     assert abs((xb * R.src_areas).sum() / (x * R.src_areas).sum() - 1) < 1e-12
+
+
+COINCIDENT = [
+    ("healpix8 nested<-ring", lambda: (grids.healpix_spec(8, "nested"), grids.healpix_spec(8, "ring"))),
+    ("healpix32 nested<-ring", lambda: (grids.healpix_spec(32, "nested"), grids.healpix_spec(32, "ring"))),
+    ("healpix128 nested<-ring", lambda: (grids.healpix_spec(128, "nested"), grids.healpix_spec(128, "ring"))),
+    ("healpix16<-healpix64", lambda: (grids.healpix_spec(16, "ring"), grids.healpix_spec(64, "ring"))),
+    ("lonlat90x45 onto itself", lambda: (grids.lonlat_spec(90, 45), grids.lonlat_spec(90, 45))),
+    ("lonlat45x30<-lonlat360x180", lambda: (grids.lonlat_spec(45, 30), grids.lonlat_spec(360, 180))),
+    ("C8<-C32", lambda: (grids.cubed_sphere_spec(8), grids.cubed_sphere_spec(32))),
+]
+
+
+@pytest.mark.parametrize("name,make", COINCIDENT, ids=[c[0] for c in COINCIDENT])
+def test_coincident_edges_identical_and_nested_grids(gpu, name, make):
+    """Identical cells in another order and exactly nested refinements: every clip line carries
+    subject vertices whose signed distances are rounding noise.  The matrix must still reproduce
+    the cell areas on both sides (a crossing at an end of an edge is that vertex -- geom.cuh)."""
+    dst, src = make()
+    R = Regridder(dst, src)
+    A = R.intersections.tocsr()
+    assert np.allclose(np.asarray(A.sum(1)).ravel(), R.dst_areas, rtol=1e-9, atol=0)
+    assert np.allclose(np.asarray(A.sum(0)).ravel(), R.src_areas, rtol=1e-9, atol=0)
