@@ -617,7 +617,7 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
         kern<<<ceil_div(n_cand, NT_), NT_, smem, st>>>(gd.view, gs.view, pairs.p, n_cand, R->opts.area_threshold,     \
                                                        pair_area.p, tile_count.p);                                    \
     } while (0)
-        if (quad) CRG_CLIP(128, 8, true, 1);
+        if (quad) CRG_CLIP(128, QUAD_SLOTS, true, 1);
         else if (fixed4) CRG_CLIP(128, 8, false, 2);
         else CRG_CLIP(64, 2 * CRG_MAX_VERTS, false, 2);
 #undef CRG_CLIP

@@ -254,30 +254,58 @@ struct Crossing {
     }
 };
 
+// The working polygon is SYMBOLIC: a 32-bit word of 4-bit vertex ids (up to 8 vertices) into a
+// per-thread table of 12 points in shared memory -- ids 0..3 are the subject cell's corners, every
+// clip pass appends at most two crossing points.  A pass computes the signed distances of the
+// current vertices (static unrolled reads), and
+//   * all inside  -> nothing to do (no copy),          * all outside -> empty,
+//   * one inside run (the convex case) -> the new polygon is that run followed by the exit and the
+//     enter crossing: a rotate/mask of the id word, and BOTH crossing points are computed in one
+//     straight-line block, so the lanes of a warp do the expensive arithmetic together,
+//   * several runs (round-off on degenerate input) -> sequential Sutherland-Hodgman over the ids.
+// A crossing within CLIP_SNAP of an end of its edge reuses that vertex's id (exact coordinates).
+constexpr int QUAD_SLOTS = 12;
+
+template <int DIM, int NT>
+struct PointTable {
+    double *b;   // this thread's column: b[(id * DIM + c) * NT]
+    __device__ __forceinline__ double get(int id, int c) const { return b[(id * DIM + c) * NT]; }
+    __device__ __forceinline__ void set(int id, int c, double x) { b[(id * DIM + c) * NT] = x; }
+};
+
+// Which vertex id stands for the crossing of edge p -> q (distances dp, dq of different sign)?
+// -1: none (the crossing is a vertex that is part of the inside run anyway), idp / idq: that end
+// vertex itself (kept as the boundary point), -2: a new point.
+__device__ __forceinline__ int crossing_kind(double dp, double dq, bool p_inside, int idp, int idq) {
+    const double adp = fabs(dp), adq = fabs(dq);
+    if (adq <= CLIP_SNAP * adp) return p_inside ? idq : -1;     // at q
+    if (adp <= CLIP_SNAP * adq) return p_inside ? -1 : idp;     // at p
+    return -2;
+}
+
 template <int DIM, int NT>
 __device__ double clip_quad_area(const CellsView &gs, int64_t s, const CellsView &gc, int64_t c,
-                                 double *smem /* 8 * DIM * NT doubles */) {
-    constexpr int MAXW = 8;
-    PolyBuf<DIM, NT, MAXW> cur{smem + threadIdx.x};
+                                 double *smem /* QUAD_SLOTS * DIM * NT doubles */) {
+    PointTable<DIM, NT> tab{smem + threadIdx.x};
     {
         double sv[4][DIM];
         load_quad<DIM>(gs.verts + s * 4 * DIM, gs.flip && gs.flip[s], sv);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int k = 0; k < DIM; ++k) cur.set(i, k, sv[i][k]);
+            for (int k = 0; k < DIM; ++k) tab.set(i, k, sv[i][k]);
     }
-    // The clip cell is NOT kept in registers (24 of them): each pass fetches the one new end of its
-    // edge (an L1 hit -- consecutive pairs share the destination cell) and keeps the other.
+    uint32_t poly = 0x3210u;     // vertex i = nibble i
+    int m = 4, nv = 4;
+    // clip cell: each pass fetches the one new end of its edge (an L1 hit -- consecutive pairs
+    // share the destination cell) and keeps the other
     const double *cbase = gc.verts + c * 4 * DIM;
     const bool cflip = gc.flip && gc.flip[c];
     double u[3], v[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int k = 0; k < DIM; ++k) v[k] = __ldg(cbase + (cflip ? 3 : 0) * DIM + k);
-    int m = 4;
-#pragma unroll
+#pragma unroll 1
     for (int e = 0; e < 4; ++e) {
-        if (m == 0) break;
         const int vi = (e + 1) & 3;
 #pragma unroll
         for (int k = 0; k < DIM; ++k) { u[k] = v[k]; v[k] = __ldg(cbase + (cflip ? 3 - vi : vi) * DIM + k); }
@@ -291,69 +319,109 @@ __device__ double clip_quad_area(const CellsView &gs, int64_t s, const CellsView
             nx = -ey; ny = ex;
             h0 = -(nx * u[0] + ny * u[1]);
         }
-        // registers: L = last vertex, (q1, q2) = the next two input vertices
-        const double Lx = cur.get(m - 1, 0), Ly = cur.get(m - 1, 1), Lz = DIM == 3 ? cur.get(m - 1, 2) : 0.0;
-        double q1x = cur.get(0, 0), q1y = cur.get(0, 1), q1z = DIM == 3 ? cur.get(0, 2) : 0.0;
-        double q2x = Lx, q2y = Ly, q2z = Lz;
-        if (m > 2) { q2x = cur.get(1, 0); q2y = cur.get(1, 1); q2z = DIM == 3 ? cur.get(1, 2) : 0.0; }
-        double px = Lx, py = Ly, pz = Lz;
-        double dp = DIM == 3 ? fma(nx, px, fma(ny, py, nz * pz)) : fma(nx, px, fma(ny, py, h0));
-        int mo = 0;
-        for (int i = 0; i < m; ++i) {
-            const double qx = q1x, qy = q1y, qz = q1z;
-            q1x = q2x; q1y = q2y; q1z = q2z;
-            if (i + 2 < m - 1) { q2x = cur.get(i + 2, 0); q2y = cur.get(i + 2, 1); q2z = DIM == 3 ? cur.get(i + 2, 2) : 0.0; }
-            else { q2x = Lx; q2y = Ly; q2z = Lz; }
-            const double dq = DIM == 3 ? fma(nx, qx, fma(ny, qy, nz * qz)) : fma(nx, qx, fma(ny, qy, h0));
-            const bool in_p = dp >= 0.0, in_q = dq >= 0.0;
-            if (in_p != in_q && mo <= i + 2 && mo < MAXW) {
-                // A crossing within CLIP_SNAP of an end of the edge IS that vertex: reuse its exact
-                // coordinates (or emit nothing when the vertex is emitted anyway) instead of a
-                // rounded near-duplicate.  On coincident edges (identical or nested grids) the
-                // distances are rounding noise; near-duplicates there classify inconsistently in
-                // the later passes and the vertex count outgrows the in-place buffer.
-                const double adp = fabs(dp), adq = fabs(dq);
-                double rx = qx, ry = qy, rz = qz;
-                bool emit = true;
-                if (adq <= CLIP_SNAP * adp) emit = !in_q;                      // at q (q inside: emitted below)
-                else if (adp <= CLIP_SNAP * adq) { emit = !in_p; rx = px; ry = py; rz = pz; }   // at p
-                else {
-                    Crossing<DIM> c;
-                    c.px = px; c.py = py; c.pz = pz; c.qx = qx; c.qy = qy; c.qz = qz; c.dp = dp; c.dq = dq;
-                    c.point(rx, ry, rz);
-                }
-                if (emit) {
-                    cur.set(mo, 0, rx); cur.set(mo, 1, ry);
-                    if (DIM == 3) cur.set(mo, 2, rz);
-                    ++mo;
-                }
+        auto dist = [&](int id) -> double {
+            if (DIM == 3) return fma(nx, tab.get(id, 0), fma(ny, tab.get(id, 1), nz * tab.get(id, 2)));
+            return fma(nx, tab.get(id, 0), fma(ny, tab.get(id, 1), h0));
+        };
+        uint32_t mask = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < m && dist((poly >> (4 * i)) & 15u) >= 0.0) mask |= 1u << i;
+        const uint32_t full = (1u << m) - 1u;
+        if (mask == full) continue;
+        if (mask == 0u) return 0.0;
+        const uint32_t next_in = ((mask >> 1) | (mask << (m - 1))) & full;    // bit i: vertex i+1 is inside
+        const uint32_t exits = mask & ~next_in;                                 // i inside, i+1 outside
+        const uint32_t enters = ~mask & next_in & full;                         // i outside, i+1 inside
+        auto nib = [&](int i) -> int { return (int)((poly >> (4 * i)) & 15u); };
+        if (__popc(exits) == 1) {
+            const int i_out = __ffs(exits) - 1, i_in = __ffs(enters) - 1;
+            int k = __popc(mask);                                               // 1 <= k <= m - 1 <= 7
+            const int rot = i_in + 1 == m ? 0 : i_in + 1;                       // first vertex of the inside run
+            uint32_t np = rot ? ((poly >> (4 * rot)) | (poly << (4 * (m - rot)))) : poly;
+            np &= (1u << (4 * k)) - 1u;
+            const int p0 = nib(i_out), q0 = nib(i_out + 1 == m ? 0 : i_out + 1);   // exit edge (p inside)
+            const int p1 = nib(i_in), q1 = rot ? nib(rot) : nib(0);               // enter edge (q inside)
+            Crossing<DIM> X0, X1;
+            X0.px = tab.get(p0, 0); X0.py = tab.get(p0, 1); X0.pz = DIM == 3 ? tab.get(p0, 2) : 0.0;
+            X0.qx = tab.get(q0, 0); X0.qy = tab.get(q0, 1); X0.qz = DIM == 3 ? tab.get(q0, 2) : 0.0;
+            X1.px = tab.get(p1, 0); X1.py = tab.get(p1, 1); X1.pz = DIM == 3 ? tab.get(p1, 2) : 0.0;
+            X1.qx = tab.get(q1, 0); X1.qy = tab.get(q1, 1); X1.qz = DIM == 3 ? tab.get(q1, 2) : 0.0;
+            X0.dp = DIM == 3 ? fma(nx, X0.px, fma(ny, X0.py, nz * X0.pz)) : fma(nx, X0.px, fma(ny, X0.py, h0));
+            X0.dq = DIM == 3 ? fma(nx, X0.qx, fma(ny, X0.qy, nz * X0.qz)) : fma(nx, X0.qx, fma(ny, X0.qy, h0));
+            X1.dp = DIM == 3 ? fma(nx, X1.px, fma(ny, X1.py, nz * X1.pz)) : fma(nx, X1.px, fma(ny, X1.py, h0));
+            X1.dq = DIM == 3 ? fma(nx, X1.qx, fma(ny, X1.qy, nz * X1.qz)) : fma(nx, X1.qx, fma(ny, X1.qy, h0));
+            double r0x, r0y, r0z, r1x, r1y, r1z;
+            X0.point(r0x, r0y, r0z);
+            X1.point(r1x, r1y, r1z);
+            int id0 = crossing_kind(X0.dp, X0.dq, true, p0, q0);
+            int id1 = crossing_kind(X1.dp, X1.dq, false, p1, q1);
+            if (id0 == -2) {
+                id0 = nv++;
+                tab.set(id0, 0, r0x); tab.set(id0, 1, r0y);
+                if (DIM == 3) tab.set(id0, 2, r0z);
             }
-            if (in_q && mo <= i + 2 && mo < MAXW) {
-                cur.set(mo, 0, qx); cur.set(mo, 1, qy);
-                if (DIM == 3) cur.set(mo, 2, qz);
-                ++mo;
+            if (id1 == -2) {
+                id1 = nv++;
+                tab.set(id1, 0, r1x); tab.set(id1, 1, r1y);
+                if (DIM == 3) tab.set(id1, 2, r1z);
             }
-            dp = dq; px = qx; py = qy; pz = qz;
+            if (id0 >= 0) { np |= (uint32_t)id0 << (4 * k); ++k; }
+            if (id1 >= 0 && id1 != id0) { np |= (uint32_t)id1 << (4 * k); ++k; }
+            poly = np;
+            m = k;
+        } else {
+            // several inside runs: sequential pass over the ids
+            uint32_t np = 0;
+            int mo = 0;
+            for (int i = 0; i < m; ++i) {
+                const int j = i + 1 == m ? 0 : i + 1;
+                const bool in_p = (mask >> i) & 1u, in_q = (mask >> j) & 1u;
+                const int idp = nib(i), idq = nib(j);
+                if (in_p != in_q) {
+                    Crossing<DIM> X;
+                    X.px = tab.get(idp, 0); X.py = tab.get(idp, 1); X.pz = DIM == 3 ? tab.get(idp, 2) : 0.0;
+                    X.qx = tab.get(idq, 0); X.qy = tab.get(idq, 1); X.qz = DIM == 3 ? tab.get(idq, 2) : 0.0;
+                    X.dp = dist(idp); X.dq = dist(idq);
+                    int id = crossing_kind(X.dp, X.dq, in_p, idp, idq);
+                    if (id == -2 && nv < QUAD_SLOTS) {
+                        double rx, ry, rz;
+                        X.point(rx, ry, rz);
+                        id = nv++;
+                        tab.set(id, 0, rx); tab.set(id, 1, ry);
+                        if (DIM == 3) tab.set(id, 2, rz);
+                    }
+                    if (id >= 0 && mo < 8) { np |= (uint32_t)id << (4 * mo); ++mo; }
+                }
+                if (in_q && mo < 8) { np |= (uint32_t)idq << (4 * mo); ++mo; }
+            }
+            poly = np;
+            m = mo;
         }
-        m = mo;
+        if (m < 3) return 0.0;
     }
     if (m < 3) return 0.0;
+    const int ia = (int)(poly & 15u);
     if (DIM == 3) {
         ExcessAcc acc;
-        const d3 a = {cur.get(0, 0), cur.get(0, 1), cur.get(0, 2)};
-        d3 b = {cur.get(1, 0), cur.get(1, 1), cur.get(1, 2)};
+        const d3 a = {tab.get(ia, 0), tab.get(ia, 1), tab.get(ia, 2)};
+        int ib = (int)((poly >> 4) & 15u);
+        d3 b = {tab.get(ib, 0), tab.get(ib, 1), tab.get(ib, 2)};
         for (int i = 2; i < m; ++i) {
-            const d3 cc = {cur.get(i, 0), cur.get(i, 1), cur.get(i, 2)};
+            const int ic = (int)((poly >> (4 * i)) & 15u);
+            const d3 cc = {tab.get(ic, 0), tab.get(ic, 1), tab.get(ic, 2)};
             acc.add_triangle(a, b, cc);
             b = cc;
         }
         return acc.area();
     } else {
         double sarea = 0.0;
-        const double x0 = cur.get(0, 0), y0 = cur.get(0, 1);
-        double ax = cur.get(1, 0) - x0, ay = cur.get(1, 1) - y0;
+        const double x0 = tab.get(ia, 0), y0 = tab.get(ia, 1);
+        const int ib = (int)((poly >> 4) & 15u);
+        double ax = tab.get(ib, 0) - x0, ay = tab.get(ib, 1) - y0;
         for (int i = 2; i < m; ++i) {
-            const double bx = cur.get(i, 0) - x0, by = cur.get(i, 1) - y0;
+            const int ic = (int)((poly >> (4 * i)) & 15u);
+            const double bx = tab.get(ic, 0) - x0, by = tab.get(ic, 1) - y0;
             sarea += ax * by - ay * bx;
             ax = bx; ay = by;
         }
