@@ -287,36 +287,57 @@ template <int DIM, int NT>
 __device__ double clip_quad_area(const CellsView &gs, int64_t s, const CellsView &gc, int64_t c,
                                  double *smem /* QUAD_SLOTS * DIM * NT doubles */) {
     PointTable<DIM, NT> tab{smem + threadIdx.x};
+    const double *cbase = gc.verts + c * 4 * DIM;
+    const bool cflip = gc.flip && gc.flip[c];
+    // Pre-pass over the ORIGINAL corners (static, every lane busy): the clip edges that leave all
+    // four subject corners inside can never cut (the working polygon only shrinks), one that leaves
+    // all four outside empties the intersection (most false candidates end here).  Afterwards a lane
+    // only visits ITS cutting edges, so the lanes of a warp meet in the cut code even when they are
+    // cut by different edges.
+    uint32_t cut = 0;
     {
-        double sv[4][DIM];
+        double sv[4][DIM], cv[4][DIM];
         load_quad<DIM>(gs.verts + s * 4 * DIM, gs.flip && gs.flip[s], sv);
+        load_quad<DIM>(cbase, cflip, cv);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int k = 0; k < DIM; ++k) tab.set(i, k, sv[i][k]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const double *u = cv[e], *v = cv[(e + 1) & 3];
+            double nx, ny, nz = 0.0, h0 = 0.0;
+            if (DIM == 3) {
+                nx = u[1] * v[2] - u[2] * v[1]; ny = u[2] * v[0] - u[0] * v[2]; nz = u[0] * v[1] - u[1] * v[0];
+            } else {
+                nx = -(v[1] - u[1]); ny = v[0] - u[0];
+                h0 = -(nx * u[0] + ny * u[1]);
+            }
+            uint32_t me = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double d = DIM == 3 ? fma(nx, sv[i][0], fma(ny, sv[i][1], nz * sv[i][2]))
+                                          : fma(nx, sv[i][0], fma(ny, sv[i][1], h0));
+                if (d >= 0.0) me |= 1u << i;
+            }
+            if (me == 0u) return 0.0;
+            if (me != 15u) cut |= 1u << e;       // (a zero-length edge has n = 0: every d = 0, never cuts)
+        }
     }
     uint32_t poly = 0x3210u;     // vertex i = nibble i
     int m = 4, nv = 4;
-    // clip cell: each pass fetches the one new end of its edge (an L1 hit -- consecutive pairs
-    // share the destination cell) and keeps the other
-    const double *cbase = gc.verts + c * 4 * DIM;
-    const bool cflip = gc.flip && gc.flip[c];
-    double u[3], v[3] = {0.0, 0.0, 0.0};
+    while (cut) {
+        const int e = __ffs(cut) - 1;
+        cut &= cut - 1u;
+        const int iu = cflip ? 3 - e : e, iv = cflip ? 3 - ((e + 1) & 3) : (e + 1) & 3;
+        double u[3] = {0.0, 0.0, 0.0}, v[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-    for (int k = 0; k < DIM; ++k) v[k] = __ldg(cbase + (cflip ? 3 : 0) * DIM + k);
-#pragma unroll 1
-    for (int e = 0; e < 4; ++e) {
-        const int vi = (e + 1) & 3;
-#pragma unroll
-        for (int k = 0; k < DIM; ++k) { u[k] = v[k]; v[k] = __ldg(cbase + (cflip ? 3 - vi : vi) * DIM + k); }
+        for (int k = 0; k < DIM; ++k) { u[k] = __ldg(cbase + iu * DIM + k); v[k] = __ldg(cbase + iv * DIM + k); }
         double nx, ny, nz = 0.0, h0 = 0.0;
         if (DIM == 3) {
             nx = u[1] * v[2] - u[2] * v[1]; ny = u[2] * v[0] - u[0] * v[2]; nz = u[0] * v[1] - u[1] * v[0];
-            if (nx == 0.0 && ny == 0.0 && nz == 0.0) continue;   // zero-length edge (pole cells)
         } else {
-            const double ex = v[0] - u[0], ey = v[1] - u[1];
-            if (ex == 0.0 && ey == 0.0) continue;
-            nx = -ey; ny = ex;
+            nx = -(v[1] - u[1]); ny = v[0] - u[0];
             h0 = -(nx * u[0] + ny * u[1]);
         }
         auto dist = [&](int id) -> double {
