@@ -609,17 +609,25 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
         const bool fixed4 = !dst->offsets && !src->offsets && dst->nv <= 4 && src->nv <= 4;
         const bool quad = allow_quad && fixed4 && dst->nv == 4 && src->nv == 4 &&
                           ((uintptr_t)gd.view.verts % 16 == 0) && ((uintptr_t)gs.view.verts % 16 == 0);
-#define CRG_CLIP(NT_, MW_, QUAD_, NBUF_)                                                                              \
+#define CRG_CLIP(NT_, MW_)                                                                                            \
     do {                                                                                                              \
-        const size_t smem = sizeof(double) * NBUF_ * MW_ * DIM * NT_;                                                 \
-        auto kern = clip_kernel<DIM, NT_, MW_, QUAD_>;                                                                \
+        const size_t smem = sizeof(double) * 2 * MW_ * DIM * NT_;                                                     \
+        auto kern = clip_kernel<DIM, NT_, MW_>;                                                                       \
         CRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
         kern<<<ceil_div(n_cand, NT_), NT_, smem, st>>>(gd.view, gs.view, pairs.p, n_cand, R->opts.area_threshold,     \
                                                        pair_area.p, tile_count.p);                                    \
     } while (0)
-        if (quad) CRG_CLIP(128, QUAD_SLOTS, true, 1);
-        else if (fixed4) CRG_CLIP(128, 8, false, 2);
-        else CRG_CLIP(64, 2 * CRG_MAX_VERTS, false, 2);
+        if (quad) {
+            constexpr int NT = 128;
+            const size_t smem = sizeof(double) * QUAD_SLOTS * DIM * NT;
+            auto kern = clip_quad_kernel<DIM, NT>;
+            CRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // an untouched source cell contributes its own area: reuse K0's (only when they are unit-sphere areas)
+            const double *unit_src_areas = r2 == 1.0 ? R->src_areas.p : nullptr;
+            kern<<<ceil_div(ceil_div(n_cand, CLIP_CHUNK), NT / 32), NT, smem, st>>>(
+                gd.view, gs.view, pairs.p, n_cand, R->opts.area_threshold, unit_src_areas, pair_area.p, tile_count.p);
+        } else if (fixed4) CRG_CLIP(128, 8);
+        else CRG_CLIP(64, 2 * CRG_MAX_VERTS);
 #undef CRG_CLIP
         CRG_LAUNCH_CHECK();
         CRG_TRY((exclusive_scan<uint32_t, uint32_t>(tile_count.p, ntiles, tile_count.p, st)));

@@ -283,46 +283,54 @@ __device__ __forceinline__ int crossing_kind(double dp, double dq, bool p_inside
     return -2;
 }
 
+// Pre-pass over the ORIGINAL corners (static code, every lane busy): a clip edge that leaves all
+// four subject corners inside can never cut (the working polygon only shrinks); one that leaves all
+// four outside empties the intersection (most false candidates end here).
+// Returns -1 (empty) or the 4-bit set of clip edges that cut.
+template <int DIM>
+__device__ __forceinline__ int quad_prepass(const CellsView &gs, int64_t s, const CellsView &gc, int64_t c) {
+    double sv[4][DIM], cv[4][DIM];
+    load_quad<DIM>(gs.verts + s * 4 * DIM, gs.flip && gs.flip[s], sv);
+    load_quad<DIM>(gc.verts + c * 4 * DIM, gc.flip && gc.flip[c], cv);
+    uint32_t cut = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const double *u = cv[e], *v = cv[(e + 1) & 3];
+        double nx, ny, nz = 0.0, h0 = 0.0;
+        if (DIM == 3) {
+            nx = u[1] * v[2] - u[2] * v[1]; ny = u[2] * v[0] - u[0] * v[2]; nz = u[0] * v[1] - u[1] * v[0];
+        } else {
+            nx = -(v[1] - u[1]); ny = v[0] - u[0];
+            h0 = -(nx * u[0] + ny * u[1]);
+        }
+        uint32_t me = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double d = DIM == 3 ? fma(nx, sv[i][0], fma(ny, sv[i][1], nz * sv[i][2]))
+                                      : fma(nx, sv[i][0], fma(ny, sv[i][1], h0));
+            if (d >= 0.0) me |= 1u << i;
+        }
+        if (me == 0u) return -1;
+        if (me != 15u) cut |= 1u << e;       // (a zero-length edge has n = 0: every d = 0, never cuts)
+    }
+    return (int)cut;
+}
+
+// Area of subject ∩ clip given the set of cutting clip edges (quad_prepass).  A lane only visits ITS
+// cutting edges, so the lanes of a warp meet in the cut code even when different edges cut them.
 template <int DIM, int NT>
-__device__ double clip_quad_area(const CellsView &gs, int64_t s, const CellsView &gc, int64_t c,
-                                 double *smem /* QUAD_SLOTS * DIM * NT doubles */) {
+__device__ double quad_cut_area(const CellsView &gs, int64_t s, const CellsView &gc, int64_t c, uint32_t cut,
+                                double *smem /* QUAD_SLOTS * DIM * NT doubles */) {
     PointTable<DIM, NT> tab{smem + threadIdx.x};
     const double *cbase = gc.verts + c * 4 * DIM;
     const bool cflip = gc.flip && gc.flip[c];
-    // Pre-pass over the ORIGINAL corners (static, every lane busy): the clip edges that leave all
-    // four subject corners inside can never cut (the working polygon only shrinks), one that leaves
-    // all four outside empties the intersection (most false candidates end here).  Afterwards a lane
-    // only visits ITS cutting edges, so the lanes of a warp meet in the cut code even when they are
-    // cut by different edges.
-    uint32_t cut = 0;
     {
-        double sv[4][DIM], cv[4][DIM];
+        double sv[4][DIM];
         load_quad<DIM>(gs.verts + s * 4 * DIM, gs.flip && gs.flip[s], sv);
-        load_quad<DIM>(cbase, cflip, cv);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int k = 0; k < DIM; ++k) tab.set(i, k, sv[i][k]);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const double *u = cv[e], *v = cv[(e + 1) & 3];
-            double nx, ny, nz = 0.0, h0 = 0.0;
-            if (DIM == 3) {
-                nx = u[1] * v[2] - u[2] * v[1]; ny = u[2] * v[0] - u[0] * v[2]; nz = u[0] * v[1] - u[1] * v[0];
-            } else {
-                nx = -(v[1] - u[1]); ny = v[0] - u[0];
-                h0 = -(nx * u[0] + ny * u[1]);
-            }
-            uint32_t me = 0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double d = DIM == 3 ? fma(nx, sv[i][0], fma(ny, sv[i][1], nz * sv[i][2]))
-                                          : fma(nx, sv[i][0], fma(ny, sv[i][1], h0));
-                if (d >= 0.0) me |= 1u << i;
-            }
-            if (me == 0u) return 0.0;
-            if (me != 15u) cut |= 1u << e;       // (a zero-length edge has n = 0: every d = 0, never cuts)
-        }
     }
     uint32_t poly = 0x3210u;     // vertex i = nibble i
     int m = 4, nv = 4;

@@ -23,7 +23,7 @@ namespace crg {
 constexpr int CLIP_TILE = 1024;      // pairs per compaction tile
 
 // QUAD = true: both cells are quadrilaterals stored with a fixed stride (fast path).
-template <int DIM, int NT, int MAXW, bool QUAD>
+template <int DIM, int NT, int MAXW>
 __global__ void __launch_bounds__(NT) clip_kernel(CellsView gd, CellsView gs, const int2 *__restrict__ pairs,
                                                   int64_t npairs, double thresh, double *__restrict__ area_out,
                                                   uint32_t *__restrict__ tile_count) {
@@ -32,13 +32,73 @@ __global__ void __launch_bounds__(NT) clip_kernel(CellsView gd, CellsView gs, co
     double area = 0.0;
     if (idx < npairs) {
         const int2 pr = pairs[idx];
-        area = QUAD ? clip_quad_area<DIM, NT>(gs, pr.x, gd, pr.y, clip_smem)
-                    : clip_pair_area<DIM, NT, MAXW>(gs, pr.x, gd, pr.y, clip_smem);
+        area = clip_pair_area<DIM, NT, MAXW>(gs, pr.x, gd, pr.y, clip_smem);
         if (!(area > thresh) || !(area > 0.0)) area = 0.0;     // `area > 0` (intersection_areas.jl:24); NaN drops too
         area_out[idx] = area;
     }
     const unsigned mask = __ballot_sync(CRG_FULL, area != 0.0);
     if ((threadIdx.x & 31) == 0 && mask) atomicAdd(&tile_count[idx / CLIP_TILE], (uint32_t)__popc(mask));
+}
+
+// Quadrilateral x quadrilateral (every structured grid of BASELINE.json), geom.cuh's symbolic clip.
+// A warp owns CLIP_CHUNK consecutive candidate pairs and alternates between two stages, without
+// block barriers:
+//   1. 32 pairs at a time, every lane runs the static pre-pass of one pair: empty (area 0, written at
+//      once), untouched (the source cell's own area, when K0's unit-sphere areas are at hand) or the
+//      set of cutting edges; the surviving pairs are appended to the warp's queue in shared memory;
+//   2. whenever 32 jobs are queued, every lane takes one and runs the cuts + the area -- full warps
+//      although a third of the candidates are false and a quarter of the rest is not cut at all.
+// Every pair's area is written exactly once; the non-zero count goes to the tile counter at the end.
+constexpr int CLIP_CHUNK = 256;     // divides CLIP_TILE
+template <int DIM, int NT>
+__global__ void __launch_bounds__(NT) clip_quad_kernel(CellsView gd, CellsView gs, const int2 *__restrict__ pairs,
+                                                       int64_t npairs, double thresh,
+                                                       const double *__restrict__ unit_src_areas,
+                                                       double *__restrict__ area_out, uint32_t *__restrict__ tile_count) {
+    extern __shared__ double clip_smem[];
+    __shared__ uint32_t s_queue[NT / 32][64];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t base = ((int64_t)blockIdx.x * (NT / 32) + wid) * CLIP_CHUNK;
+    if (base >= npairs) return;
+    uint32_t *queue = s_queue[wid];
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int qn = 0, nz = 0;
+#pragma unroll 1
+    for (int round = 0; round <= CLIP_CHUNK / 32; ++round) {        // the extra round only drains the queue
+        const int64_t idx = base + round * 32 + lane;
+        int state = -1;
+        if (round < CLIP_CHUNK / 32 && idx < npairs) {
+            const int2 pr = pairs[idx];
+            state = quad_prepass<DIM>(gs, pr.x, gd, pr.y);
+            double area = 0.0;
+            if (state == 0 && unit_src_areas) { area = unit_src_areas[pr.x]; state = -1; }
+            if (state < 0) {
+                if (!(area > thresh) || !(area > 0.0)) area = 0.0;
+                area_out[idx] = area;
+                nz += area != 0.0;
+            }
+        }
+        const unsigned surv = __ballot_sync(CRG_FULL, state >= 0);
+        if (state >= 0) queue[qn + __popc(surv & lt_mask)] = (uint32_t)(round * 32 + lane) | ((uint32_t)state << 8);
+        qn += __popc(surv);
+        __syncwarp();
+        const int take = qn >= 32 ? 32 : (round == CLIP_CHUNK / 32 ? qn : 0);
+        if (take) {
+            qn -= take;
+            if (lane < take) {
+                const uint32_t j = queue[qn + lane];
+                const int64_t jdx = base + (j & 255u);
+                const int2 pr = pairs[jdx];
+                double area = quad_cut_area<DIM, NT>(gs, pr.x, gd, pr.y, j >> 8, clip_smem);
+                if (!(area > thresh) || !(area > 0.0)) area = 0.0;     // `area > 0` (intersection_areas.jl:24); NaN drops too
+                area_out[jdx] = area;
+                nz += area != 0.0;
+            }
+            __syncwarp();
+        }
+    }
+    nz = warp_sum(nz);
+    if (lane == 0 && nz) atomicAdd(&tile_count[base / CLIP_TILE], (uint32_t)nz);
 }
 
 // Stable compaction of the surviving pairs of one tile: tile_off = exclusive scan of tile_count.
