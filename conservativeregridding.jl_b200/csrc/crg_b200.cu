@@ -199,6 +199,18 @@ static int alloc_csr(Csr &M, int64_t n_rows, int64_t n_cols, int64_t nnz, cudaSt
     return CRG_OK;
 }
 
+// rowptr[r] = first entry of the row-sorted keys whose row is >= r  (kernels.cuh: heads, then search)
+static int make_rowptr(const uint64_t *keys, int64_t nnz, int64_t n_rows, int32_t *rowptr, cudaStream_t st) {
+    CRG_CUDA(cudaMemsetAsync(rowptr, 0xFF, sizeof(int32_t) * (size_t)(n_rows + 1), st));
+    if (nnz > 0) {
+        rowptr_heads_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(keys, nnz, rowptr);
+        CRG_LAUNCH_CHECK();
+    }
+    rowptr_kernel<<<ceil_div(n_rows + 1, 256), 256, 0, st>>>(keys, nnz, n_rows, rowptr);
+    CRG_LAUNCH_CHECK();
+    return CRG_OK;
+}
+
 // CSR -> SELL-32-sigma (sell.cuh): window sort, slice offsets, piece list, scatter.
 static int build_sell(Csr &M, cudaStream_t st) {
     M.sell_npieces = 0;
@@ -284,8 +296,7 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
         R->nnz = nnz;
         CRG_TRY(alloc_csr(A, R->n_dst, R->n_src, nnz, st));
         if (nnz > 0) {
-            rowptr_kernel<<<ceil_div(A.n_rows + 1, 256), 256, 0, st>>>(ka, nnz, A.n_rows, A.rowptr.p);
-            CRG_LAUNCH_CHECK();
+            CRG_TRY(make_rowptr(ka, nnz, A.n_rows, A.rowptr.p, st));
             row_sort_split_kernel<<<ceil_div(A.n_rows, ROWSORT_ROWS), ROWSORT_ROWS, 0, st>>>(ka, (double *)va, A.rowptr.p, A.n_rows, A.colidx.p, A.vals.p);
             CRG_LAUNCH_CHECK();
         }
@@ -302,8 +313,7 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
                 CRG_LAUNCH_CHECK();
                 split_csr_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(kb, (const double *)va, nnz, T.colidx.p, T.vals.p);
                 CRG_LAUNCH_CHECK();
-                rowptr_kernel<<<ceil_div(T.n_rows + 1, 256), 256, 0, st>>>(kb, nnz, T.n_rows, T.rowptr.p);
-                CRG_LAUNCH_CHECK();
+                CRG_TRY(make_rowptr(kb, nnz, T.n_rows, T.rowptr.p, st));
             }
             CRG_TRY(finish_csr(T, st));
             R->has_At = true;
@@ -326,8 +336,7 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
                 CRG_LAUNCH_CHECK();
                 split_csr_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(kb, (const double *)va, nnz, T.colidx.p, T.vals.p);
             CRG_LAUNCH_CHECK();
-            rowptr_kernel<<<ceil_div(T.n_rows + 1, 256), 256, 0, st>>>(kb, nnz, T.n_rows, T.rowptr.p);
-                CRG_LAUNCH_CHECK();
+            CRG_TRY(make_rowptr(kb, nnz, T.n_rows, T.rowptr.p, st));
             }
             CRG_TRY(finish_csr(T, st));
             R->has_At = true;
@@ -343,8 +352,7 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
         if (nnz > 0) {
             split_csr_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(ka, (const double *)va, nnz, A.colidx.p, A.vals.p);
             CRG_LAUNCH_CHECK();
-            rowptr_kernel<<<ceil_div(A.n_rows + 1, 256), 256, 0, st>>>(ka, nnz, A.n_rows, A.rowptr.p);
-            CRG_LAUNCH_CHECK();
+            CRG_TRY(make_rowptr(ka, nnz, A.n_rows, A.rowptr.p, st));
         }
         CRG_TRY(finish_csr(A, st));
         *t_sort_csc1 = (int)tm.ev.size();
@@ -380,8 +388,7 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
     if (nnz > 0) {
         split_csr_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(ka, (const double *)va, nnz, A.colidx.p, A.vals.p);
             CRG_LAUNCH_CHECK();
-            rowptr_kernel<<<ceil_div(A.n_rows + 1, 256), 256, 0, st>>>(ka, nnz, A.n_rows, A.rowptr.p);
-        CRG_LAUNCH_CHECK();
+            CRG_TRY(make_rowptr(ka, nnz, A.n_rows, A.rowptr.p, st));
     }
     CRG_TRY(finish_csr(A, st));
     *t_sort_csr1 = (int)tm.ev.size();
@@ -395,8 +402,7 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
             if (inb) { std::swap(ka, kb); std::swap(va, vb); }
             split_csr_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(ka, (const double *)va, nnz, T.colidx.p, T.vals.p);
             CRG_LAUNCH_CHECK();
-            rowptr_kernel<<<ceil_div(T.n_rows + 1, 256), 256, 0, st>>>(ka, nnz, T.n_rows, T.rowptr.p);
-            CRG_LAUNCH_CHECK();
+            CRG_TRY(make_rowptr(ka, nnz, T.n_rows, T.rowptr.p, st));
         }
         CRG_TRY(finish_csr(T, st));
         R->stats.sort_passes_csc = p3;

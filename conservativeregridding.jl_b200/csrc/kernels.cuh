@@ -182,12 +182,27 @@ __global__ void __launch_bounds__(256) split_csr_kernel(const uint64_t *__restri
     colidx[i] = (int32_t)(uint32_t)keys[i];
     ovals[i] = vals[i];
 }
-// ... and the row pointers: rowptr[r] = first entry whose row is >= r (binary search per row, so that
-// runs of empty rows -- half the rows of a destination-sharded transpose block -- cost nothing extra).
+// ... and the row pointers: rowptr[r] = first entry whose row is >= r.  Two launches over a rowptr
+// array preset to -1: (a) one thread per ENTRY -- the first entry of a row writes its own index, and
+// also the pointers of up to ROWPTR_GAP empty rows just before it (coalesced key reads, no search);
+// (b) one thread per ROW -- rows still at -1 (inside longer runs of empty rows: half the rows of a
+// destination-sharded transpose block, or past the last entry) are found by binary search.
+constexpr int ROWPTR_GAP = 4;
+__global__ void __launch_bounds__(256) rowptr_heads_kernel(const uint64_t *__restrict__ keys, int64_t nnz,
+                                                           int32_t *__restrict__ rowptr) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnz) return;
+    const int64_t r = (int64_t)(keys[i] >> 32);
+    const int64_t rp = i == 0 ? -1 : (int64_t)(keys[i - 1] >> 32);
+    if (r == rp) return;
+    const int64_t lo = max(rp + 1, r - ROWPTR_GAP);
+    for (int64_t q = lo; q <= r; ++q) rowptr[q] = (int32_t)i;
+}
 __global__ void __launch_bounds__(256) rowptr_kernel(const uint64_t *__restrict__ keys, int64_t nnz, int64_t n_rows,
                                                      int32_t *__restrict__ rowptr) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r > n_rows) return;
+    if (rowptr[r] >= 0) return;
     int64_t lo = 0, hi = nnz;
     while (lo < hi) {
         const int64_t mid = (lo + hi) >> 1;
@@ -195,6 +210,7 @@ __global__ void __launch_bounds__(256) rowptr_kernel(const uint64_t *__restrict_
     }
     rowptr[r] = (int32_t)lo;
 }
+
 
 // Row-grouped COO with short rows -> CSR: a block stages the entries of its ROWSORT_ROWS rows in
 // shared memory (coalesced), one thread per row sorts its entries by column (insertion sort; the
