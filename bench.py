@@ -136,7 +136,7 @@ def run_reference(args, rank):
     oracle.build()
     desc, fd, fs = WORKLOADS[args.workload]
     dst, src = fd(grids).materialize(), fs(grids).materialize()
-    nthreads = oracle.max_threads()
+    nthreads = oracle.use_all_cores()          # torchrun exports OMP_NUM_THREADS=1
     trees = (oracle.treeify(dst), oracle.treeify(src))
     x = np.random.default_rng(20260101).random(src.ncells)
     times = []
@@ -352,7 +352,7 @@ def main():
             by_t = None
         apply_f_gbs = by_f / (fwd_ms * 1e-3) / 1e9 if world == 1 else None
         apply_t_gbs = by_t / (bwd_ms * 1e-3) / 1e9 if world == 1 else None
-        roof_clip = {"kernel": "clip_kernel<3,128,8,true>", "bound": "fp64", "achieved": clip_tflops, "peak": fp64_peak,
+        roof_clip = {"kernel": "clip_quad_kernel<3,128>", "bound": "fp64", "achieved": clip_tflops, "peak": fp64_peak,
                      "unit": "TFLOP/s", "frac": clip_tflops / fp64_peak if fp64_peak else None, "traffic": None,
                      "peak_source": "crg_fp64_peak DFMA micro-benchmark, measured in this run",
                      "flops_per_pair": flops_per_pair, "pairs": n_cand, "ms": clip_ms,
@@ -382,7 +382,7 @@ def main():
             # largest share of the step is the FP64-bound clip kernel, reported beside it in `roofline_clip`
             "roofline": roof_apply if roof_apply else roof_clip,
             "roofline_clip": roof_clip, "roofline_apply": roof_apply,
-            "dominant_kernel_by_time": "clip_kernel (FP64-bound, see roofline_clip): %.0f%% of the step" % (100 * clip_ms / ms_per_step),
+            "dominant_kernel_by_time": "clip_quad_kernel (FP64-bound, see roofline_clip): %.0f%% of the step" % (100 * clip_ms / ms_per_step),
             "gpu_launches": launches, "clocks": clocks,
             "conservation_error": max(cons, cons_T),
         }
@@ -489,7 +489,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle
         oracle.build()
-        nthreads = oracle.max_threads()
+        nthreads = oracle.use_all_cores()
         trees = (oracle.treeify(dst), oracle.treeify(src))
         t0 = time.perf_counter()
         Rc, tcpu = cpu_reference_step(oracle, dst, src, trees, x_host, nthreads)
@@ -508,9 +508,10 @@ def main():
         dist.destroy_process_group()
 
 
-# FP64 flops per candidate pair of clip_kernel<3,128,8,true> on the cfg5 workload, counted from the SASS page
-# of the ncu capture summarised in profiles/README.md (124.6 DFMA x 2 + 62.8 DMUL + 27.6 DADD per pair).
-CLIP_FLOPS_PER_PAIR = 339.6
+# FP64 flops per candidate pair of clip_quad_kernel<3,128> on the cfg5 workload, counted from the SASS page
+# of the ncu capture summarised in profiles/README.md (119.9 DFMA x 2 + 81.1 DMUL + 18.0 DADD per pair;
+# the first, division-based kernel of this round executed 339.6).
+CLIP_FLOPS_PER_PAIR = 338.8
 # dram__bytes_read.sum + dram__bytes_write.sum of one forward spmv launch on cfg5 (ncu --set full)
 SPMV_TRAFFIC_BYTES = 161645824
 

@@ -538,3 +538,12 @@ int orc_max_threads(void) {
     return 1;
 #endif
 }
+
+/* Launchers such as torchrun export OMP_NUM_THREADS=1; the CPU baseline asks for the cores it may use. */
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

@@ -79,6 +79,8 @@ def lib():
         L.orc_free.restype = None
         L.orc_free.argtypes = [C.c_void_p]
         L.orc_max_threads.restype = C.c_int
+        L.orc_set_threads.argtypes = [C.c_int]
+        L.orc_set_threads.restype = None
         _lib = L
     return _lib
 
@@ -103,6 +105,14 @@ def _grid_args(g):
 
 def max_threads() -> int:
     return int(lib().orc_max_threads())
+
+
+def use_all_cores() -> int:
+    """Let OpenMP use every core this process may run on (torchrun exports OMP_NUM_THREADS=1)."""
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().orc_set_threads(C.c_int(n))
+    return max_threads()
 
 
 # ----------------------------------------------------------------------------
