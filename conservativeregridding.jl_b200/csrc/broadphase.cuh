@@ -49,6 +49,7 @@ struct BPParams {
     double inv_hq;           // BP_SUB / bin size
     double eps;              // box inflation
     double big_chord;        // diameter threshold of "big" cells (chord length / planar length)
+    float u_reject;          // a face cannot see a (non-big) cell whose first vertex has |u| or |v| above this
 };
 
 struct QBox { int x0, x1, y0, y1; };
@@ -93,6 +94,14 @@ __device__ __forceinline__ bool cell_face_qbox(const double *p, int n, int face,
         const int ax = face >> 1;
         const float sg = (face & 1) ? -1.f : 1.f;
         const int bx = ax == 2 ? 0 : ax + 1, cx = bx == 2 ? 0 : bx + 1;
+        {   // quick reject on the first vertex (three of the six faces fail the sign test, most of the
+            // others this one): whenever the box test below accepts, every vertex lies within
+            // 4 cell diameters of azimuth of the extended face domain
+            const float w0 = sg * (float)p[ax];
+            if (!(w0 > (float)BP_MIN_W)) return false;
+            const float lim = P.u_reject * w0;
+            if (fabsf((float)p[bx]) > lim || fabsf((float)p[cx]) > lim) return false;
+        }
         float fa0 = 2.f, fa1 = -2.f, fb0 = 2.f, fb1 = -2.f;
         for (int i = 0; i < n; ++i) {
             const float w = sg * (float)p[3 * i + ax];
@@ -230,13 +239,16 @@ __global__ void __launch_bounds__(256) bp_bin_kernel(CellsView g, const float *_
     const double *p = stage_cell<DIM>(g, c, &n, stage);
     if (c >= g.ncells) return;
     bool big = DIM == 3 && !(diam[c] < (float)P.big_chord);
-    if (!big) {     // total number of bins the cell would be inserted in (boxes are recomputed below: cheaper
-        int cover = 0;  // than keeping six of them in local memory)
+    unsigned faces = 0;          // faces that see the cell
+    if (!big) {     // total number of bins the cell would be inserted in (the boxes of the one or two faces
+        int cover = 0;  // that see it are recomputed below: cheaper than keeping them in local memory)
         for (int f = 0; f < P.nfaces; ++f) {
             QBox b;
             bool cl;
-            if (cell_face_qbox<DIM>(p, n, f, P, &b, &cl))
+            if (cell_face_qbox<DIM>(p, n, f, P, &b, &cl)) {
                 cover += ((b.x1 >> 4) - (b.x0 >> 4) + 1) * ((b.y1 >> 4) - (b.y0 >> 4) + 1);
+                faces |= 1u << f;
+            }
         }
         big = cover > BP_MAX_COVER;
     }
@@ -244,7 +256,9 @@ __global__ void __launch_bounds__(256) bp_bin_kernel(CellsView g, const float *_
         if (!FILL) big_list[atomicAdd(big_counter, 1u)] = (int32_t)c;
         return;
     }
-    for (int f = 0; f < P.nfaces; ++f) {
+    while (faces) {
+        const int f = __ffs(faces) - 1;
+        faces &= faces - 1u;
         QBox b;
         bool cl;
         if (!cell_face_qbox<DIM>(p, n, f, P, &b, &cl)) continue;

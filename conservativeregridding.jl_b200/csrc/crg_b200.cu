@@ -505,6 +505,11 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
         P.hx = P.hy = F;
         P.inv_hq = BP_SUB / (2.0 * F / nb);
         P.eps = 1e-6;
+        {   // quick-reject bound of cell_face_qbox: tan(A + 4 * largest non-big cell diameter as an angle)
+            const double dmax = std::fmax((double)hst[0].max_diam, (double)hst[1].max_diam);
+            const double ang = A + 4.0 * 2.0 * std::asin(std::fmin(1.0, 0.5 * dmax));
+            P.u_reject = (float)(std::tan(std::fmin(ang, 1.5)) * (1.0 + 1e-5));
+        }
         S.bin_size = h;
     } else {
         P.nfaces = 1;
@@ -530,6 +535,7 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
         P.nby = (int)std::fmin((double)NB_CAP, std::fmax(1.0, std::ceil(Ly / h)));
         P.inv_hq = BP_SUB / h;
         P.big_chord = 1e300;
+        P.u_reject = 3.0e38f;
         S.bin_size = h;
     }
     const size_t nbins = (size_t)P.nfaces * P.nbx * P.nby;
