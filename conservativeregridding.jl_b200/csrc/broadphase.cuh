@@ -28,6 +28,9 @@ constexpr int BP_SUB = 16;              // quantisation: sub-bins per bin
 constexpr int BP_MAX_BINS_1D = 4095;    // so that quantised coordinates fit 16 bits
 constexpr int BP_MAX_COVER = 4096;      // a source cell covering more bins is "big"
 constexpr int BP_MAX_QUERY = 1 << 18;   // a destination cell covering more bins is "big"
+#ifndef BP_QUERY_MINB
+#define BP_QUERY_MINB 10
+#endif
 constexpr int BP_SHORT_ROW = 48;        // rows with at most this many candidates are column-sorted by one thread
 constexpr double BP_BIG_ANGLE = 0.2;    // rad; larger spherical cells are "big"
 constexpr double BP_MIN_W = 0.05;       // a face is usable only if all vertices have w > this
@@ -143,15 +146,15 @@ __device__ __forceinline__ const double *cell_ptr(const CellsView &g, int64_t c,
 // padded shared-memory tile and every thread reads its cell from there.  Must be called by all
 // threads of the block (blockDim.x <= 256); returns this thread's cell (shared or global memory).
 constexpr int STAGE_THREADS = 256;
-template <int DIM>
+template <int DIM, int NT = STAGE_THREADS>
 struct CellStage {
     static constexpr int CELL = 4 * DIM;          // doubles per quad
     static constexpr int PAD = CELL + 1;          // padded stride: conflict-free 8-byte reads
-    double tile[STAGE_THREADS * PAD];
+    double tile[NT * PAD];
 };
-template <int DIM>
-__device__ __forceinline__ const double *stage_cell(const CellsView &g, int64_t c, int *n, CellStage<DIM> &S) {
-    constexpr int CELL = CellStage<DIM>::CELL, PAD = CellStage<DIM>::PAD, CHUNKS = CELL / 2;
+template <int DIM, int NT>
+__device__ __forceinline__ const double *stage_cell(const CellsView &g, int64_t c, int *n, CellStage<DIM, NT> &S) {
+    constexpr int CELL = CellStage<DIM, NT>::CELL, PAD = CellStage<DIM, NT>::PAD, CHUNKS = CELL / 2;
     const bool fast = !g.off && g.nv == 4 && ((uintptr_t)g.verts % 16 == 0);     // block-uniform
     if (!fast) {
         if (c >= g.ncells) { *n = 0; return g.verts; }
@@ -288,7 +291,7 @@ __device__ __forceinline__ int home_face(const double *p, int n) {
 // FILL = true : pairs[cand_off[d] + k] = (src, d); big destination cells are skipped (filled by
 //               bp_fill_big_dst_kernel).
 template <int DIM, bool FILL>
-__global__ void __launch_bounds__(128) bp_query_kernel(CellsView g, const float *__restrict__ diam, BPParams P,
+__global__ void __launch_bounds__(128, BP_QUERY_MINB) bp_query_kernel(CellsView g, const float *__restrict__ diam, BPParams P,
                                                        const uint32_t *__restrict__ bin_start,
                                                        const int4 *__restrict__ entries,
                                                        const int32_t *__restrict__ big_src, int n_big_src,
@@ -296,7 +299,7 @@ __global__ void __launch_bounds__(128) bp_query_kernel(CellsView g, const float 
                                                        const int64_t *__restrict__ cand_off,
                                                        int2 *__restrict__ pairs, int32_t *__restrict__ big_dst,
                                                        uint32_t *__restrict__ big_dst_counter) {
-    __shared__ CellStage<DIM> stage;
+    __shared__ CellStage<DIM, 128> stage;
     const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int n;
     const double *p = stage_cell<DIM>(g, d, &n, stage);
