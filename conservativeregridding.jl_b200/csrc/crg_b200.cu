@@ -199,14 +199,22 @@ static int alloc_csr(Csr &M, int64_t n_rows, int64_t n_cols, int64_t nnz, cudaSt
     return CRG_OK;
 }
 
-// rowptr[r] = first entry of the row-sorted keys whose row is >= r  (kernels.cuh: heads, then search)
-static int make_rowptr(const uint64_t *keys, int64_t nnz, int64_t n_rows, int32_t *rowptr, cudaStream_t st) {
-    CRG_CUDA(cudaMemsetAsync(rowptr, 0xFF, sizeof(int32_t) * (size_t)(n_rows + 1), st));
-    if (nnz > 0) {
-        rowptr_heads_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(keys, nnz, rowptr);
+// Sorted triples -> rowptr (+ colidx, vals when `split`) of M; low = the triples are in (col, row) order and
+// M is the transpose (kernels.cuh: csr_split_kernel, rowptr_kernel).
+static int fill_csr(Csr &M, const uint64_t *keys, const double *vals, int64_t nnz, bool low, bool split, cudaStream_t st) {
+    CRG_CUDA(cudaMemsetAsync(M.rowptr.p, 0xFF, sizeof(int32_t) * (size_t)(M.n_rows + 1), st));
+    const int g = ceil_div(nnz, 256), gr = ceil_div(M.n_rows + 1, 256);
+    if (low) {
+        if (split) csr_split_kernel<true, true><<<g, 256, 0, st>>>(keys, vals, nnz, M.rowptr.p, M.colidx.p, M.vals.p);
+        else csr_split_kernel<true, false><<<g, 256, 0, st>>>(keys, vals, nnz, M.rowptr.p, M.colidx.p, M.vals.p);
         CRG_LAUNCH_CHECK();
+        rowptr_kernel<true><<<gr, 256, 0, st>>>(keys, nnz, M.n_rows, M.rowptr.p);
+    } else {
+        if (split) csr_split_kernel<false, true><<<g, 256, 0, st>>>(keys, vals, nnz, M.rowptr.p, M.colidx.p, M.vals.p);
+        else csr_split_kernel<false, false><<<g, 256, 0, st>>>(keys, vals, nnz, M.rowptr.p, M.colidx.p, M.vals.p);
+        CRG_LAUNCH_CHECK();
+        rowptr_kernel<false><<<gr, 256, 0, st>>>(keys, nnz, M.n_rows, M.rowptr.p);
     }
-    rowptr_kernel<<<ceil_div(n_rows + 1, 256), 256, 0, st>>>(keys, nnz, n_rows, rowptr);
     CRG_LAUNCH_CHECK();
     return CRG_OK;
 }
@@ -296,7 +304,7 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
         R->nnz = nnz;
         CRG_TRY(alloc_csr(A, R->n_dst, R->n_src, nnz, st));
         if (nnz > 0) {
-            CRG_TRY(make_rowptr(ka, nnz, A.n_rows, A.rowptr.p, st));
+            CRG_TRY(fill_csr(A, ka, nullptr, nnz, false, false, st));
             row_sort_split_kernel<<<ceil_div(A.n_rows, ROWSORT_ROWS), ROWSORT_ROWS, 0, st>>>(ka, (double *)va, A.rowptr.p, A.n_rows, A.colidx.p, A.vals.p);
             CRG_LAUNCH_CHECK();
         }
@@ -309,11 +317,7 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
             if (inb) { std::swap(ka, kb); std::swap(va, vb); }
             CRG_TRY(alloc_csr(T, R->n_src, R->n_dst, nnz, st));
             if (nnz > 0) {
-                swap_key_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(ka, nnz, kb);      // kb = col<<32 | row
-                CRG_LAUNCH_CHECK();
-                split_csr_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(kb, (const double *)va, nnz, T.colidx.p, T.vals.p);
-                CRG_LAUNCH_CHECK();
-                CRG_TRY(make_rowptr(kb, nnz, T.n_rows, T.rowptr.p, st));
+                CRG_TRY(fill_csr(T, ka, (const double *)va, nnz, true, true, st));      // (col, row) order: rows of A^T = low word
             }
             CRG_TRY(finish_csr(T, st));
             R->has_At = true;
@@ -332,11 +336,7 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
         if (R->opts.build_transpose) {
             CRG_TRY(alloc_csr(T, R->n_src, R->n_dst, nnz, st));
             if (nnz > 0) {
-                swap_key_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(ka, nnz, kb);      // kb = col<<32 | row
-                CRG_LAUNCH_CHECK();
-                split_csr_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(kb, (const double *)va, nnz, T.colidx.p, T.vals.p);
-            CRG_LAUNCH_CHECK();
-            CRG_TRY(make_rowptr(kb, nnz, T.n_rows, T.rowptr.p, st));
+                CRG_TRY(fill_csr(T, ka, (const double *)va, nnz, true, true, st));      // (col, row) order: rows of A^T = low word
             }
             CRG_TRY(finish_csr(T, st));
             R->has_At = true;
@@ -350,9 +350,7 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
         R->stats.sort_passes_csr = p2;
         CRG_TRY(alloc_csr(A, R->n_dst, R->n_src, nnz, st));
         if (nnz > 0) {
-            split_csr_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(ka, (const double *)va, nnz, A.colidx.p, A.vals.p);
-            CRG_LAUNCH_CHECK();
-            CRG_TRY(make_rowptr(ka, nnz, A.n_rows, A.rowptr.p, st));
+            CRG_TRY(fill_csr(A, ka, (const double *)va, nnz, false, true, st));
         }
         CRG_TRY(finish_csr(A, st));
         *t_sort_csc1 = (int)tm.ev.size();
@@ -386,9 +384,7 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
     R->nnz = nnz;
     CRG_TRY(alloc_csr(A, R->n_dst, R->n_src, nnz, st));
     if (nnz > 0) {
-        split_csr_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(ka, (const double *)va, nnz, A.colidx.p, A.vals.p);
-            CRG_LAUNCH_CHECK();
-            CRG_TRY(make_rowptr(ka, nnz, A.n_rows, A.rowptr.p, st));
+        CRG_TRY(fill_csr(A, ka, (const double *)va, nnz, false, true, st));
     }
     CRG_TRY(finish_csr(A, st));
     *t_sort_csr1 = (int)tm.ev.size();
@@ -400,9 +396,7 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
             CRG_LAUNCH_CHECK();
             CRG_TRY(radix_sort_pairs(ka, va, kb, vb, nnz, 32, 32 + bits_src, &inb, &p3, st));
             if (inb) { std::swap(ka, kb); std::swap(va, vb); }
-            split_csr_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(ka, (const double *)va, nnz, T.colidx.p, T.vals.p);
-            CRG_LAUNCH_CHECK();
-            CRG_TRY(make_rowptr(ka, nnz, T.n_rows, T.rowptr.p, st));
+            CRG_TRY(fill_csr(T, ka, (const double *)va, nnz, false, true, st));
         }
         CRG_TRY(finish_csr(T, st));
         R->stats.sort_passes_csc = p3;

@@ -173,31 +173,35 @@ __global__ void __launch_bounds__(256) swap_key_kernel(const uint64_t *__restric
     if (i < n) { const uint64_t k = in[i]; out[i] = (k << 32) | (k >> 32); }
 }
 
-// keys sorted by (row << 32 | col): write col indices and values ...
-__global__ void __launch_bounds__(256) split_csr_kernel(const uint64_t *__restrict__ keys,
-                                                        const double *__restrict__ vals, int64_t nnz,
+// Sorted triples -> CSR.  keys = row << 32 | col; the triples are sorted by (row, col) [LOW = false: CSR of
+// A] or by (col, row) [LOW = true: CSR of A^T, whose rows are the columns -- no swapped key copy is made].
+//   csr_split_kernel: one thread per ENTRY writes the CSR column index and value; the first entry of a
+//     row also writes the row pointer of its row and of up to ROWPTR_GAP empty rows just before it
+//     (coalesced key reads, no search) into a rowptr array preset to -1;
+//   rowptr_kernel: one thread per ROW -- rows still at -1 (inside longer runs of empty rows: half the
+//     rows of a destination-sharded transpose block, or past the last entry) are found by binary search.
+constexpr int ROWPTR_GAP = 4;
+template <bool LOW>
+__device__ __forceinline__ int64_t key_row(uint64_t k) { return LOW ? (int64_t)(uint32_t)k : (int64_t)(k >> 32); }
+
+template <bool LOW, bool SPLIT>
+__global__ void __launch_bounds__(256) csr_split_kernel(const uint64_t *__restrict__ keys, const double *__restrict__ vals,
+                                                        int64_t nnz, int32_t *__restrict__ rowptr,
                                                         int32_t *__restrict__ colidx, double *__restrict__ ovals) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nnz) return;
-    colidx[i] = (int32_t)(uint32_t)keys[i];
-    ovals[i] = vals[i];
-}
-// ... and the row pointers: rowptr[r] = first entry whose row is >= r.  Two launches over a rowptr
-// array preset to -1: (a) one thread per ENTRY -- the first entry of a row writes its own index, and
-// also the pointers of up to ROWPTR_GAP empty rows just before it (coalesced key reads, no search);
-// (b) one thread per ROW -- rows still at -1 (inside longer runs of empty rows: half the rows of a
-// destination-sharded transpose block, or past the last entry) are found by binary search.
-constexpr int ROWPTR_GAP = 4;
-__global__ void __launch_bounds__(256) rowptr_heads_kernel(const uint64_t *__restrict__ keys, int64_t nnz,
-                                                           int32_t *__restrict__ rowptr) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nnz) return;
-    const int64_t r = (int64_t)(keys[i] >> 32);
-    const int64_t rp = i == 0 ? -1 : (int64_t)(keys[i - 1] >> 32);
+    const uint64_t k = keys[i];
+    if (SPLIT) {
+        colidx[i] = LOW ? (int32_t)(k >> 32) : (int32_t)(uint32_t)k;
+        ovals[i] = vals[i];
+    }
+    const int64_t r = key_row<LOW>(k);
+    const int64_t rp = i == 0 ? -1 : key_row<LOW>(keys[i - 1]);
     if (r == rp) return;
     const int64_t lo = max(rp + 1, r - ROWPTR_GAP);
     for (int64_t q = lo; q <= r; ++q) rowptr[q] = (int32_t)i;
 }
+template <bool LOW>
 __global__ void __launch_bounds__(256) rowptr_kernel(const uint64_t *__restrict__ keys, int64_t nnz, int64_t n_rows,
                                                      int32_t *__restrict__ rowptr) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -206,11 +210,10 @@ __global__ void __launch_bounds__(256) rowptr_kernel(const uint64_t *__restrict_
     int64_t lo = 0, hi = nnz;
     while (lo < hi) {
         const int64_t mid = (lo + hi) >> 1;
-        if ((int64_t)(keys[mid] >> 32) < r) lo = mid + 1; else hi = mid;
+        if (key_row<LOW>(keys[mid]) < r) lo = mid + 1; else hi = mid;
     }
     rowptr[r] = (int32_t)lo;
 }
-
 
 // Row-grouped COO with short rows -> CSR: a block stages the entries of its ROWSORT_ROWS rows in
 // shared memory (coalesced), one thread per row sorts its entries by column (insertion sort; the
