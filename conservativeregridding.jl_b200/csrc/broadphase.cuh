@@ -183,9 +183,12 @@ __device__ __forceinline__ const double *stage_cell(const CellsView &g, int64_t 
 }
 
 // --- bounds: per-cell diameter + grid statistics -----------------------------------------
+// K4 + K1 in one pass over the vertices: geometric area (x scale) and orientation flag of every cell
+// (regridder.jl:165-178), its diameter, and the grid statistics the bin grid is chosen from.
 template <int DIM>
 __global__ void __launch_bounds__(256) bp_bounds_kernel(CellsView g, float *__restrict__ diam, BPStats *st,
-                                                        float big_chord) {
+                                                        float big_chord, double scale, double *__restrict__ areas,
+                                                        uint8_t *__restrict__ flip, unsigned int *__restrict__ nflip) {
     __shared__ CellStage<DIM> stage;
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double sum = 0.0, lo0 = 1e300, lo1 = 1e300, hi0 = -1e300, hi1 = -1e300;
@@ -194,6 +197,11 @@ __global__ void __launch_bounds__(256) bp_bounds_kernel(CellsView g, float *__re
     int n;
     const double *p = stage_cell<DIM>(g, c, &n, stage);
     if (c < g.ncells) {
+        const double a = polygon_signed_area<DIM>(p, n);
+        areas[c] = fabs(a) * scale;
+        const bool f = a < 0.0;
+        flip[c] = f ? 1 : 0;
+        if (f) atomicAdd(nflip, 1u);
         const float d = cell_diameter<DIM>(p, n);
         diam[c] = d;
         if (DIM == 2 || d < big_chord) { sum = d; mx = d; cnt = 1; }

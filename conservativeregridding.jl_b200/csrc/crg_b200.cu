@@ -451,10 +451,6 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     DevBuf<unsigned int> nflip;
     CRG_TRY(nflip.alloc_tmp(2, st));
     CRG_CUDA(cudaMemsetAsync(nflip.p, 0, 2 * sizeof(unsigned int), st));
-    if (nd) { cell_area_kernel<DIM><<<ceil_div(nd, 256), 256, 0, st>>>(gd.view, r2, R->dst_areas.p, gd.flip.p, nflip.p); CRG_LAUNCH_CHECK(); }
-    if (ns) { cell_area_kernel<DIM><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, r2, R->src_areas.p, gs.flip.p, nflip.p + 1); CRG_LAUNCH_CHECK(); }
-    gd.view.flip = gd.flip.p;
-    gs.view.flip = gs.flip.p;
     CRG_TRY(tm.mark());   // 1
 
     // ---- K1: bounds -------------------------------------------------------------------------
@@ -467,8 +463,11 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     for (int k = 0; k < 2; ++k) { hst[k].lo[0] = hst[k].lo[1] = ~0ull; hst[k].hi[0] = hst[k].hi[1] = 0ull; }
     CRG_CUDA(cudaMemcpyAsync(dstats.p, hst, sizeof(hst), cudaMemcpyHostToDevice, st));
     const double big_chord = 2.0 * std::sin(BP_BIG_ANGLE / 2.0);
-    if (nd) { bp_bounds_kernel<DIM><<<ceil_div(nd, 256), 256, 0, st>>>(gd.view, gd.diam.p, dstats.p, (float)big_chord); CRG_LAUNCH_CHECK(); }
-    if (ns) { bp_bounds_kernel<DIM><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, gs.diam.p, dstats.p + 1, (float)big_chord); CRG_LAUNCH_CHECK(); }
+    // (the views' flip pointers are still null here: the kernel sees the cells as stored)
+    if (nd) { bp_bounds_kernel<DIM><<<ceil_div(nd, 256), 256, 0, st>>>(gd.view, gd.diam.p, dstats.p, (float)big_chord, r2, R->dst_areas.p, gd.flip.p, nflip.p); CRG_LAUNCH_CHECK(); }
+    if (ns) { bp_bounds_kernel<DIM><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, gs.diam.p, dstats.p + 1, (float)big_chord, r2, R->src_areas.p, gs.flip.p, nflip.p + 1); CRG_LAUNCH_CHECK(); }
+    gd.view.flip = gd.flip.p;
+    gs.view.flip = gs.flip.p;
     CRG_CUDA(cudaMemcpyAsync(hst, dstats.p, sizeof(hst), cudaMemcpyDeviceToHost, st));
     CRG_CUDA(cudaStreamSynchronize(st));
     CRG_TRY(tm.mark());   // 2

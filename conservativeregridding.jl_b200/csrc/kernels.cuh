@@ -127,23 +127,7 @@ __global__ void __launch_bounds__(256) compact_pairs_kernel(const int2 *__restri
         }
 }
 
-// =======================================================================================
-// K4: per-cell geometric area (regridder.jl:165-178) + orientation flags.
-// =======================================================================================
-template <int DIM>
-__global__ void __launch_bounds__(256) cell_area_kernel(CellsView g, double scale, double *__restrict__ areas,
-                                                        uint8_t *__restrict__ flip, unsigned int *__restrict__ nflip) {
-    __shared__ CellStage<DIM> stage;
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int n;
-    const double *p = stage_cell<DIM>(g, c, &n, stage);
-    if (c >= g.ncells) return;
-    const double a = polygon_signed_area<DIM>(p, n);
-    areas[c] = fabs(a) * scale;
-    const bool f = a < 0.0;
-    flip[c] = f ? 1 : 0;
-    if (f) atomicAdd(nflip, 1u);
-}
+// (K4, per-cell geometric area + orientation flags, is fused into bp_bounds_kernel -- broadphase.cuh)
 
 // =======================================================================================
 // K5 helpers: duplicate summation, key swap, CSR split.
