@@ -19,6 +19,7 @@
 // Entries carry the source cell's box quantised to 1/16 bin, so the query rejects
 // non-overlapping boxes without touching the source vertices.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 #include "geom.cuh"
 
@@ -40,7 +41,8 @@ constexpr double BP_MIN_W = 0.05;       // a face is usable only if all vertices
 struct BPStats {
     double sum_diam;
     unsigned long long count;
-    unsigned long long lo[2], hi[2];   // order-preserving encodings of the planar bounding box
+    unsigned long long lo[3], hi[3];   // order-preserving encodings of the bounding box of the vertices
+                                       // (planar: x, y of every cell; sphere: x, y, z of the non-big cells)
     float max_diam;
     int pad;
 };
@@ -55,6 +57,8 @@ struct BPParams {
     double eps;              // box inflation
     double big_chord;        // diameter threshold of "big" cells (chord length / planar length)
     float u_reject;          // a face cannot see a (non-big) cell whose first vertex has |u| or |v| above this
+    float cull_lo[3], cull_hi[3];   // sphere: source cells whose first vertex lies outside this box cannot meet
+                                    // any destination cell (destination-sharded builds see a slab of the globe)
 };
 
 struct QBox { int x0, x1, y0, y1; };
@@ -191,7 +195,11 @@ __global__ void __launch_bounds__(256) bp_bounds_kernel(CellsView g, float *__re
                                                         uint8_t *__restrict__ flip, unsigned int *__restrict__ nflip) {
     __shared__ CellStage<DIM> stage;
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    double sum = 0.0, lo0 = 1e300, lo1 = 1e300, hi0 = -1e300, hi1 = -1e300;
+    // bounding box of the vertices: exact (double) in the plane, where it becomes the bin-grid domain;
+    // single precision on the sphere, where it only feeds the (inflated) culling box
+    using BT = typename std::conditional<DIM == 2, double, float>::type;
+    double sum = 0.0;
+    BT lo[3] = {(BT)1e30, (BT)1e30, (BT)1e30}, hi[3] = {(BT)-1e30, (BT)-1e30, (BT)-1e30};
     float mx = 0.f;
     unsigned cnt = 0;
     int n;
@@ -204,35 +212,50 @@ __global__ void __launch_bounds__(256) bp_bounds_kernel(CellsView g, float *__re
         if (f) atomicAdd(nflip, 1u);
         const float d = cell_diameter<DIM>(p, n);
         diam[c] = d;
-        if (DIM == 2 || d < big_chord) { sum = d; mx = d; cnt = 1; }
-        if (DIM == 2)
-            for (int i = 0; i < n; ++i) {
-                lo0 = fmin(lo0, p[2 * i]); hi0 = fmax(hi0, p[2 * i]);
-                lo1 = fmin(lo1, p[2 * i + 1]); hi1 = fmax(hi1, p[2 * i + 1]);
-            }
+        if (DIM == 2 || d < big_chord) {
+            sum = d; mx = d; cnt = 1;
+            for (int i = 0; i < n; ++i)
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) {
+                    const BT x = (BT)p[DIM * i + k];
+                    lo[k] = x < lo[k] ? x : lo[k];
+                    hi[k] = x > hi[k] ? x : hi[k];
+                }
+        }
     }
     sum = warp_sum(sum); mx = warp_max(mx); cnt = warp_sum(cnt);
-    if (DIM == 2) { lo0 = warp_min(lo0); lo1 = warp_min(lo1); hi0 = warp_max(hi0); hi1 = warp_max(hi1); }
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) { lo[k] = warp_min(lo[k]); hi[k] = warp_max(hi[k]); }
     // one set of atomics per block (same-address atomics from every warp serialised at the L2)
-    __shared__ double r_sum[8], r_lo0[8], r_lo1[8], r_hi0[8], r_hi1[8];
+    __shared__ double r_sum[8];
+    __shared__ BT r_lo[3][8], r_hi[3][8];
     __shared__ float r_mx[8];
     __shared__ unsigned r_cnt[8];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) { r_sum[wid] = sum; r_mx[wid] = mx; r_cnt[wid] = cnt; r_lo0[wid] = lo0; r_lo1[wid] = lo1; r_hi0[wid] = hi0; r_hi1[wid] = hi1; }
+    if (lane == 0) {
+        r_sum[wid] = sum; r_mx[wid] = mx; r_cnt[wid] = cnt;
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) { r_lo[k][wid] = lo[k]; r_hi[k][wid] = hi[k]; }
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         const int nw = blockDim.x >> 5;
         for (int w = 1; w < nw; ++w) {
             sum += r_sum[w]; mx = fmaxf(mx, r_mx[w]); cnt += r_cnt[w];
-            lo0 = fmin(lo0, r_lo0[w]); lo1 = fmin(lo1, r_lo1[w]); hi0 = fmax(hi0, r_hi0[w]); hi1 = fmax(hi1, r_hi1[w]);
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) {
+                lo[k] = r_lo[k][w] < lo[k] ? r_lo[k][w] : lo[k];
+                hi[k] = r_hi[k][w] > hi[k] ? r_hi[k][w] : hi[k];
+            }
         }
         if (cnt) {
             atomicAdd(&st->sum_diam, sum);
             atomicAdd(&st->count, (unsigned long long)cnt);
             atomic_max_pos_float(&st->max_diam, mx);
-            if (DIM == 2) {
-                atomicMin(&st->lo[0], ordered_bits(lo0)); atomicMin(&st->lo[1], ordered_bits(lo1));
-                atomicMax(&st->hi[0], ordered_bits(hi0)); atomicMax(&st->hi[1], ordered_bits(hi1));
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) {
+                atomicMin(&st->lo[k], ordered_bits((double)lo[k]));
+                atomicMax(&st->hi[k], ordered_bits((double)hi[k]));
             }
         }
     }
@@ -252,6 +275,11 @@ __global__ void __launch_bounds__(256) bp_bin_kernel(CellsView g, const float *_
     const double *p = stage_cell<DIM>(g, c, &n, stage);
     if (c >= g.ncells) return;
     bool big = DIM == 3 && !(diam[c] < (float)P.big_chord);
+    if (DIM == 3 && !big) {
+        const float x = (float)p[0], y = (float)p[1], z = (float)p[2];
+        if (x < P.cull_lo[0] || x > P.cull_hi[0] || y < P.cull_lo[1] || y > P.cull_hi[1] || z < P.cull_lo[2] || z > P.cull_hi[2])
+            return;
+    }
     unsigned faces = 0;          // faces that see the cell
     if (!big) {     // total number of bins the cell would be inserted in (the boxes of the one or two faces
         int cover = 0;  // that see it are recomputed below: cheaper than keeping them in local memory)

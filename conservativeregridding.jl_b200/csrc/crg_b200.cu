@@ -460,7 +460,8 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     CRG_TRY(dstats.alloc_tmp(2, st));
     BPStats hst[2];
     memset(hst, 0, sizeof(hst));
-    for (int k = 0; k < 2; ++k) { hst[k].lo[0] = hst[k].lo[1] = ~0ull; hst[k].hi[0] = hst[k].hi[1] = 0ull; }
+    for (int k = 0; k < 2; ++k)
+        for (int j = 0; j < 3; ++j) { hst[k].lo[j] = ~0ull; hst[k].hi[j] = 0ull; }
     CRG_CUDA(cudaMemcpyAsync(dstats.p, hst, sizeof(hst), cudaMemcpyHostToDevice, st));
     const double big_chord = 2.0 * std::sin(BP_BIG_ANGLE / 2.0);
     // (the views' flip pointers are still null here: the kernel sees the cells as stored)
@@ -498,6 +499,18 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
         P.hx = P.hy = F;
         P.inv_hq = BP_SUB / (2.0 * F / nb);
         P.eps = 1e-6;
+        {   // Source cells that cannot meet any destination cell are not binned.  Every point of a non-big
+            // destination cell lies within the box of the destination vertices inflated by the bulge of the
+            // sphere over the cell, at most 1 - cos(diam) <= diam^2/2; a source cell meeting it has its first vertex within one source
+            // diameter (chord) of that point.  Big destination cells pair with everything: no culling.
+            const bool all_small = hst[0].count == (unsigned long long)nd && nd > 0;
+            const double dd = (double)hst[0].max_diam, ds = (double)hst[1].max_diam;
+            const double infl = ds + 0.5 * dd * dd * 1.05 + 1e-6;
+            for (int j = 0; j < 3; ++j) {
+                P.cull_lo[j] = all_small ? (float)(ordered_bits_to_double(hst[0].lo[j]) - infl) : -2.f;
+                P.cull_hi[j] = all_small ? (float)(ordered_bits_to_double(hst[0].hi[j]) + infl) : 2.f;
+            }
+        }
         {   // quick-reject bound of cell_face_qbox: tan(A + 4 * largest non-big cell diameter as an angle)
             const double dmax = std::fmax((double)hst[0].max_diam, (double)hst[1].max_diam);
             const double ang = A + 4.0 * 2.0 * std::asin(std::fmin(1.0, 0.5 * dmax));

@@ -351,3 +351,25 @@ def test_rotated_polar_and_identical_grids(gpu):
     assert np.allclose(A.diagonal(), R.dst_areas, rtol=1e-12)
     off = A - sp.diags(A.diagonal())
     assert off.nnz == 0 or abs(off).max() < 1e-12 * R.dst_areas.max()
+
+
+@pytest.mark.parametrize("dst_name,src_name,blocks", [
+    ("lonlat", "healpix", 4), ("healpix_nested", "lonlat", 3), ("cubed", "healpix", 5), ("lonlat", "cubed", 2)])
+def test_destination_blocks_equal_rows_of_the_full_matrix(gpu, dst_name, src_name, blocks):
+    """A destination-sharded build sees a slab of the globe and skips the source cells that cannot
+    reach it (culling box, crg_b200.cu): every block must reproduce its rows of the full matrix
+    bit for bit, for band-shaped (lon-lat, ring) and patch-shaped (nested, cubed-sphere) blocks."""
+    make = {"lonlat": lambda: grids.lonlat_grid(96, 48), "healpix": lambda: grids.healpix_grid(16, "ring"),
+            "healpix_nested": lambda: grids.healpix_grid(16, "nested"), "cubed": lambda: grids.cubed_sphere_grid(12)}
+    dst, src = make[dst_name](), make[src_name]()
+    full = Regridder(dst, src).intersections.tocsr()
+    n = dst.ncells
+    for k in range(blocks):
+        lo, hi = k * n // blocks, (k + 1) * n // blocks
+        R = Regridder(dst.slice(lo, hi), src)
+        blk = R.intersections.tocsr()
+        ref = full[lo:hi]
+        assert blk.shape == ref.shape
+        assert np.array_equal(blk.indptr, ref.indptr) and np.array_equal(blk.indices, ref.indices)
+        assert np.array_equal(blk.data, ref.data)
+        assert np.array_equal(R.dst_areas, Regridder(dst, src).dst_areas[lo:hi])
