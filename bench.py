@@ -513,7 +513,7 @@ def main():
 # the first, division-based kernel of this round executed 339.6).
 CLIP_FLOPS_PER_PAIR = 338.8
 # dram__bytes_read.sum + dram__bytes_write.sum of one forward spmv launch on cfg5 (ncu --set full)
-SPMV_TRAFFIC_BYTES = 161645824
+SPMV_TRAFFIC_BYTES = 158312960
 
 if __name__ == "__main__":
     main()

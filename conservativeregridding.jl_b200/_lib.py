@@ -29,7 +29,7 @@ CRG_PLANAR, CRG_SPHERICAL = 0, 1
 # every symbol include/crg_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "crg_options_init", "crg_build", "crg_build_from_coo", "crg_free", "crg_dims", "crg_stats", "crg_areas",
-    "crg_export_csc", "crg_export_csr", "crg_candidates", "crg_normalize", "crg_apply", "crg_apply_async",
+    "crg_export_csc", "crg_export_csr", "crg_candidates", "crg_normalize", "crg_maximum", "crg_scale", "crg_apply", "crg_apply_async",
     "crg_set_stream", "crg_synchronize", "crg_apply_bytes", "crg_last_error", "crg_device_count", "crg_version",
     "crg_fp64_peak", "crg_launch_count", "crg_build_grids", "crg_grid_ncells", "crg_grid_cells",
 ]
@@ -131,6 +131,8 @@ def lib():
     L.crg_export_csr.argtypes = [vp, i32, vp, vp, vp]
     L.crg_candidates.argtypes = [vp, vp, vp]
     L.crg_normalize.argtypes = [vp]
+    L.crg_maximum.argtypes = [vp, P(f64)]
+    L.crg_scale.argtypes = [vp, f64]
     L.crg_apply.argtypes = [vp, i32, i32, vp, vp, i64, i64, i64, i32]
     L.crg_apply_async.argtypes = [vp, i32, i32, vp, vp, i64, i64, i64, i32]
     L.crg_set_stream.argtypes = [vp, vp]

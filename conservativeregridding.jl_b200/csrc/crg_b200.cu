@@ -407,23 +407,37 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
     return CRG_OK;
 }
 
-static int do_normalize(crg_regridder *R) {
+// maximum(A) into R->scratch_max (device); 0 for an empty matrix
+static int device_maximum(crg_regridder *R) {
     cudaStream_t st = R->stream;
-    if (R->nnz == 0) return CRG_OK;   // maximum() of an empty matrix: nothing to scale
     CRG_TRY(R->scratch_max.alloc(1, st));
     CRG_CUDA(cudaMemsetAsync(R->scratch_max.p, 0, sizeof(double), st));
-    max_kernel<<<296, 256, 0, st>>>(R->A.vals.p, R->nnz, R->scratch_max.p);
-    CRG_LAUNCH_CHECK();
-    div_by_kernel<<<296, 256, 0, st>>>(R->A.vals.p, R->nnz, R->scratch_max.p);
-    CRG_LAUNCH_CHECK();
-    if (R->has_At) { div_by_kernel<<<296, 256, 0, st>>>(R->At.vals.p, R->nnz, R->scratch_max.p); CRG_LAUNCH_CHECK(); }
-    for (Csr *M : {&R->A, &R->At})
-        if (M->sell_padded > 0) { div_by_kernel<<<296, 256, 0, st>>>(M->sell_vals.p, M->sell_padded, R->scratch_max.p); CRG_LAUNCH_CHECK(); }
-    div_by_kernel<<<148, 256, 0, st>>>(R->dst_areas.p, R->n_dst, R->scratch_max.p);
-    CRG_LAUNCH_CHECK();
-    div_by_kernel<<<148, 256, 0, st>>>(R->src_areas.p, R->n_src, R->scratch_max.p);
-    CRG_LAUNCH_CHECK();
+    if (R->nnz > 0) {
+        max_kernel<<<296, 256, 0, st>>>(R->A.vals.p, R->nnz, R->scratch_max.p);
+        CRG_LAUNCH_CHECK();
+    }
     return CRG_OK;
+}
+
+// A, A^T (CSR and SELL copies) and both area vectors divided by the value in R->scratch_max
+static int divide_by_scratch(crg_regridder *R) {
+    cudaStream_t st = R->stream;
+    if (R->nnz > 0) {
+        div_by_kernel<<<296, 256, 0, st>>>(R->A.vals.p, R->nnz, R->scratch_max.p);
+        CRG_LAUNCH_CHECK();
+        if (R->has_At) { div_by_kernel<<<296, 256, 0, st>>>(R->At.vals.p, R->nnz, R->scratch_max.p); CRG_LAUNCH_CHECK(); }
+        for (Csr *M : {&R->A, &R->At})
+            if (M->sell_padded > 0) { div_by_kernel<<<296, 256, 0, st>>>(M->sell_vals.p, M->sell_padded, R->scratch_max.p); CRG_LAUNCH_CHECK(); }
+    }
+    if (R->n_dst > 0) { div_by_kernel<<<148, 256, 0, st>>>(R->dst_areas.p, R->n_dst, R->scratch_max.p); CRG_LAUNCH_CHECK(); }
+    if (R->n_src > 0) { div_by_kernel<<<148, 256, 0, st>>>(R->src_areas.p, R->n_src, R->scratch_max.p); CRG_LAUNCH_CHECK(); }
+    return CRG_OK;
+}
+
+static int do_normalize(crg_regridder *R) {
+    if (R->nnz == 0) return CRG_OK;   // maximum() of an empty matrix: nothing to scale
+    CRG_TRY(device_maximum(R));
+    return divide_by_scratch(R);
 }
 
 template <int DIM>
@@ -1209,6 +1223,28 @@ int crg_normalize(crg_regridder *r) {
     DeviceGuard guard;
     CRG_TRY(guard.set(r->device));
     CRG_TRY(do_normalize(r));
+    CRG_CUDA(cudaStreamSynchronize(r->stream));
+    return CRG_OK;
+}
+
+int crg_maximum(crg_regridder *r, double *out) {
+    if (!r || !out) return set_error(CRG_ERR_INVALID, "null argument");
+    DeviceGuard guard;
+    CRG_TRY(guard.set(r->device));
+    CRG_TRY(device_maximum(r));
+    CRG_CUDA(cudaMemcpyAsync(out, r->scratch_max.p, sizeof(double), cudaMemcpyDeviceToHost, r->stream));
+    CRG_CUDA(cudaStreamSynchronize(r->stream));
+    return CRG_OK;
+}
+
+int crg_scale(crg_regridder *r, double divisor) {
+    if (!r) return set_error(CRG_ERR_INVALID, "null regridder");
+    if (!(divisor > 0.0) || !std::isfinite(divisor)) return set_error(CRG_ERR_INVALID, "divisor must be positive and finite");
+    DeviceGuard guard;
+    CRG_TRY(guard.set(r->device));
+    CRG_TRY(r->scratch_max.alloc(1, r->stream));
+    CRG_CUDA(cudaMemcpyAsync(r->scratch_max.p, &divisor, sizeof(double), cudaMemcpyHostToDevice, r->stream));
+    CRG_TRY(divide_by_scratch(r));
     CRG_CUDA(cudaStreamSynchronize(r->stream));
     return CRG_OK;
 }

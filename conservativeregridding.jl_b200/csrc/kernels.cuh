@@ -201,8 +201,7 @@ __global__ void __launch_bounds__(256) rowptr_kernel(const uint64_t *__restrict_
 
 // Row-grouped COO with short rows -> CSR: a block stages the entries of its ROWSORT_ROWS rows in
 // shared memory (coalesced), one thread per row sorts its entries by column (insertion sort; the
-// candidate lists are a few entries long), and the block writes the CSR column/value arrays and the
-// (row, col)-ordered triples (input of the column passes of the transpose) back, coalesced.
+// candidate lists are a few entries long), and the block writes the CSR column/value arrays, coalesced.
 // A block whose rows hold more than ROWSORT_CAP entries sorts in place in global memory.
 constexpr int ROWSORT_ROWS = 128;
 constexpr int ROWSORT_CAP = 2560;
@@ -246,8 +245,8 @@ __global__ void __launch_bounds__(ROWSORT_ROWS) row_sort_split_kernel(uint64_t *
         for (int i = A + threadIdx.x; i < B; i += ROWSORT_ROWS) {
             const uint64_t k = sk[i - A];
             const double v = sv[i - A];
-            keys[i] = k; vals[i] = v;
-            colidx[i] = (int32_t)(uint32_t)k; out_vals[i] = v;
+            colidx[i] = (int32_t)(uint32_t)k; out_vals[i] = v;     // (the triples themselves stay row-grouped: all the
+                                                                   //  stable column passes of the transpose need)
         }
     }
 }

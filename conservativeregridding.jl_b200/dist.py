@@ -11,6 +11,7 @@ rank; each rank builds the row block ``A_r`` of ``A`` for its destination cells 
   and the partial source vectors are summed with one all-reduce over NVLink; the division by the
   (replicated, geometric) source areas follows the reduction.
 * ``R.dst_areas``: all-gather of the per-block areas; ``R.src_areas``: computed by every rank.
+* ``normalize=True``: every block is scaled by the all-reduced (max) ``maximum(A_r)``.
 
 The reference has no distributed path at all; the single-process semantics
 this reproduces are ``Regridder`` / ``regrid!`` / ``transpose`` (src/regridder/regridder.jl:125-163,
@@ -63,6 +64,13 @@ class _LocalB200:
     def src_areas(self, device=None):      # geometric areas of the (replicated) source grid
         return self._areas("src", device)
 
+    def maximum(self) -> float:           # maximum(A_r); 0 for an empty block
+        return self.R.intersections.maximum()
+
+    def scale(self, divisor: float):      # A_r, A_r^T and both area vectors ./= divisor
+        from .regridder import scale_
+        scale_(self.R, divisor)
+
     def apply(self, out: torch.Tensor, x: torch.Tensor, normalize: bool = True):
         """out = (A_r x) ./ a_dst_r"""
         from .regridder import regrid_
@@ -82,7 +90,7 @@ class ShardedRegridder:
     numpy/scipy factory to exercise the sharding and the collectives under gloo.)"""
 
     def __init__(self, dst: Grid, src: Grid, group=None, local_factory: Optional[Callable] = None,
-                 device: Optional[torch.device] = None):
+                 device: Optional[torch.device] = None, normalize: bool = False):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -92,6 +100,14 @@ class ShardedRegridder:
         self.dst_bounds = block_bounds(self.n_dst, self.world)
         lo, hi = self.dst_bounds[self.rank]
         self.local = factory(dst.slice(lo, hi), src)
+        if normalize:
+            # normalize!(R) (regridder.jl:54-62): A, dst_areas, src_areas ./= maximum(A); the maximum of a
+            # row-sharded A is the max over the blocks' maxima -- one scalar all-reduce.
+            m = torch.tensor([self.local.maximum()], dtype=torch.float64, device=self.device)
+            if self.world > 1:
+                dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self.group)
+            if float(m.item()) > 0.0:
+                self.local.scale(float(m.item()))
         self._dst_areas = None
         self._src_areas = None
         self._nnz = None

@@ -68,7 +68,11 @@ function SparseArrays.sparse(A::B200Matrix)
 end
 SparseArrays.findnz(A::B200Matrix) = SparseArrays.findnz(SparseArrays.sparse(A))
 SparseArrays.nnz(A::B200Matrix) = SparseArrays.nnz(SparseArrays.sparse(A))
-Base.maximum(A::B200Matrix) = maximum(SparseArrays.nonzeros(SparseArrays.sparse(A)))
+function Base.maximum(A::B200Matrix)
+    m = Ref{Float64}(0.0)
+    check(ccall((:crg_maximum, lib), Cint, (Ptr{Cvoid}, Ref{Float64}), A.h, m))
+    return m[]
+end
 
 # y = A x without the area division (plain mul! semantics, used by generic code paths)
 function LinearAlgebra.mul!(y::StridedVecOrMat{Float64}, A::B200Matrix, x::StridedVecOrMat{Float64})

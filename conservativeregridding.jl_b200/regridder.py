@@ -210,8 +210,10 @@ class B200Matrix:
         return self.tocsc().toarray()
 
     def maximum(self) -> float:
-        A = self.tocsc()
-        return float(A.data.max()) if A.nnz else 0.0
+        """``maximum(A)`` (device max-reduce; 0 for an empty matrix)."""
+        m = C.c_double(0.0)
+        _lib.check(_lib.lib().crg_maximum(self._h.ptr, C.byref(m)))
+        return float(m.value)
 
     def stats(self) -> dict:
         s = _lib.BuildStats()
@@ -316,6 +318,14 @@ def areas_to(R: RegridderB200, dst_areas_out=None, src_areas_out=None):
 def normalize_(R: RegridderB200) -> RegridderB200:
     """``LinearAlgebra.normalize!(R)``: divide A and both area vectors by maximum(A)."""
     _lib.check(_lib.lib().crg_normalize(R.intersections._h.ptr))
+    _refresh_areas(R)
+    return R
+
+
+def scale_(R: RegridderB200, divisor: float) -> RegridderB200:
+    """Divide A and both area vectors by ``divisor`` -- ``normalize!`` with a given maximum (a
+    destination-sharded regridder scales every row block by the maximum over all blocks)."""
+    _lib.check(_lib.lib().crg_scale(R.intersections._h.ptr, float(divisor)))
     _refresh_areas(R)
     return R
 

@@ -166,6 +166,12 @@ int crg_candidates(const crg_regridder *r, int64_t *src_idx, int64_t *dst_idx);
 
 int crg_normalize(crg_regridder *r);
 
+/* The two halves of normalize! for destination-sharded regridders (regridder.jl:54-62 applied to a
+ * row block): crg_maximum = maximum(A) of this handle's block (0 for an empty block); crg_scale
+ * divides A, A^T and both area vectors by `divisor` (> 0) -- the maximum over all blocks.        */
+int crg_maximum(crg_regridder *r, double *out);
+int crg_scale(crg_regridder *r, double divisor);
+
 /* dst = A * src (transpose = 0) or A^T * src (transpose = 1), then divided element-wise by
  * the output grid's areas when divide_by_area != 0 (the `normalize` kw of regrid!,
  * regrid.jl:104-118), for K right-hand sides at once.

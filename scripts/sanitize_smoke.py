@@ -17,4 +17,8 @@ def poly(k):
 R3 = Regridder(grids.polygons_grid([poly(rng.integers(3, 9)) for _ in range(60)]), grids.polygons_grid([poly(rng.integers(3, 7)) for _ in range(80)]))
 R4 = regridder_from_coo(50, 40, rng.integers(0, 50, 500), rng.integers(0, 40, 500), rng.random(500) + 0.1, np.ones(50), np.ones(40))
 y4 = np.zeros(50); regrid_(y4, R4, np.ones(40))
+# identical cells (coincident edges: snapped crossings, sequential fallback), a destination block (culling box)
+R5 = Regridder(grids.healpix_grid(8, "nested"), grids.healpix_grid(8, "ring"))
+d6 = grids.lonlat_grid(48, 24)
+R6 = Regridder(d6.slice(200, 500), grids.cubed_sphere_grid(8), build_transpose=True)
 print("sanitize smoke done", R.intersections.nnz, R2.intersections.nnz, R3.intersections.nnz, R4.intersections.nnz)

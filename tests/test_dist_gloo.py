@@ -28,6 +28,14 @@ class _OracleLocal:
     def src_areas(self, device=None):
         return torch.from_numpy(self.O.src_areas.copy())
 
+    def maximum(self):
+        return float(self.A.data.max()) if self.A.nnz else 0.0
+
+    def scale(self, divisor):
+        self.A = self.A / divisor
+        self.O.dst_areas = self.O.dst_areas / divisor
+        self.O.src_areas = self.O.src_areas / divisor
+
     def apply(self, out, x, normalize=True):
         y = self.A @ x.numpy()
         if normalize:
@@ -73,6 +81,14 @@ def _worker(rank, world, port, q):
         lo, hi = block_bounds(dst.ncells, world)[rank]
         yl = S.regrid(torch.from_numpy(x0), broadcast=False, gather=False)
         assert yl.shape[0] == hi - lo and np.allclose(yl.numpy(), full.regrid(x0)[lo:hi], rtol=1e-13)
+        # normalize!(R): every block scaled by the global maximum(A) (one scalar all-reduce)
+        Sn = ShardedRegridder(dst, src, local_factory=_OracleLocal, normalize=True)
+        m = full.tocsc().max()
+        assert np.allclose(Sn.dst_areas.numpy(), full.dst_areas / m, rtol=1e-15)
+        assert np.allclose(Sn.src_areas.numpy(), full.src_areas / m, rtol=1e-15)
+        assert abs(max(Sn.local.maximum(), 0.0) - (full.tocsc()[lo:hi].max() / m)) < 1e-15
+        yn = Sn.regrid(torch.from_numpy(x0), broadcast=False)
+        assert np.allclose(yn.numpy(), full.regrid(x0), rtol=1e-13)          # the normalisation cancels in regrid!
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback

@@ -201,6 +201,14 @@ def test_normalize(gpu):
     xb, xbn = np.zeros(src.ncells), np.zeros(src.ncells)
     regrid_(xb, transpose(R), y); regrid_(xbn, transpose(Rn), y)
     assert np.allclose(xb, xbn, rtol=1e-13)
+    # the two halves used by destination-sharded regridders: device maximum, scale by a given maximum
+    assert m == R.intersections.tocsc().data.max()
+    from crg_b200.regridder import scale_
+    R3 = scale_(Regridder(dst, src), m)
+    assert np.array_equal(R3.intersections.tocsc().data, Rn.intersections.tocsc().data)
+    assert np.array_equal(R3.dst_areas, Rn.dst_areas) and np.array_equal(R3.src_areas, Rn.src_areas)
+    with pytest.raises(_lib.CrgError):
+        scale_(R3, 0.0)
 
 
 def test_ragged_clockwise_and_degenerate_cells(gpu):
