@@ -381,3 +381,34 @@ def test_destination_blocks_equal_rows_of_the_full_matrix(gpu, dst_name, src_nam
         assert np.array_equal(blk.indptr, ref.indptr) and np.array_equal(blk.indices, ref.indices)
         assert np.array_equal(blk.data, ref.data)
         assert np.array_equal(R.dst_areas, Regridder(dst, src).dst_areas[lo:hi])
+
+
+def test_four_times_the_bench_workload(gpu):
+    """0.125 deg lon-lat (4.1 M cells) <-> HEALPix 1024 (12.6 M cells): ~54 M candidate pairs, ~37 M
+    entries -- four times BASELINE config 5 in every count, to exercise the 32-bit offsets, the scans
+    and the arena well beyond the bench sizes.  Grids are generated on the device; the checks are the
+    size-independent ones: A 1 = dst areas and A^T 1 = src areas (through regrid! of ones), global-mean
+    conservation in both directions, and sum of areas = 4 pi."""
+    import torch
+    dst, src = grids.lonlat_spec(2880, 1440), grids.healpix_spec(1024, "ring")
+    R = Regridder(dst, src)
+    n_dst, n_src = R.shape
+    assert (n_dst, n_src) == (2880 * 1440, 12 * 1024 * 1024)
+    st = R.intersections.stats()
+    assert st["n_big_dst"] == 0 and st["n_big_src"] == 0
+    assert 3.0e7 < R.intersections.nnz < 4.5e7 and st["n_candidates"] < 7.0e7
+    da, sa = torch.from_numpy(R.dst_areas).cuda(), torch.from_numpy(R.src_areas).cuda()
+    assert abs(float(da.sum()) / (4 * np.pi) - 1) < 1e-12 and abs(float(sa.sum()) / (4 * np.pi) - 1) < 1e-12
+    ones_s = torch.ones(n_src, dtype=torch.float64, device="cuda")
+    y = torch.zeros(n_dst, dtype=torch.float64, device="cuda")
+    regrid_(y, R, ones_s)
+    assert float((y - 1).abs().max()) < 1e-9                           # row sums = dst areas
+    xb = torch.zeros(n_src, dtype=torch.float64, device="cuda")
+    regrid_(xb, transpose(R), torch.ones(n_dst, dtype=torch.float64, device="cuda"))
+    assert float((xb - 1).abs().max()) < 1e-9                          # column sums = src areas
+    x = torch.rand(n_src, dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(3))
+    regrid_(y, R, x)
+    assert abs(float((y * da).sum() / (x * sa).sum()) - 1) < 1e-12
+    regrid_(xb, transpose(R), y)
+    assert abs(float((xb * sa).sum() / (y * da).sum()) - 1) < 1e-12
+    print("4x cfg5: build %.2f ms device, %d candidates, %d nnz" % (st["ms_device"], st["n_candidates"], R.intersections.nnz))
