@@ -32,10 +32,27 @@ __device__ __forceinline__ d3 cross(d3 a, d3 b) {
 // sum of angles = angle of the product -- one atan2 per polygon instead of one per
 // triangle.  The product is flushed through atan2 whenever its angle could leave
 // (-pi/2, pi/2), so arbitrarily large polygons stay exact.
+// atan2(im, re).  Grid cells are small: the accumulated half-excess is almost always a tiny angle, for
+// which the odd series through x^13 is exact to double precision (|x| <= 1/32: next term < 2^-73 x);
+// everything else takes the library routine.
+__device__ __forceinline__ double atan2_general(double im, double re) { return atan2(im, re); }
+__device__ __forceinline__ double atan2_small(double im, double re) {
+    if (re > 0.0 && fabs(im) <= 0.03125 * re) {
+        const double x = im / re, t = x * x;
+        double p = fma(t, 1.0 / 13.0, -1.0 / 11.0);
+        p = fma(p, t, 1.0 / 9.0);
+        p = fma(p, t, -1.0 / 7.0);
+        p = fma(p, t, 1.0 / 5.0);
+        p = fma(p, t, -1.0 / 3.0);
+        return fma(p * t, x, x);
+    }
+    return atan2_general(im, re);
+}
+
 struct ExcessAcc {
     double re = 1.0, im = 0.0, total = 0.0;
     __device__ __forceinline__ void flush() {
-        total += atan2(im, re);
+        total += atan2_small(im, re);
         re = 1.0; im = 0.0;
     }
     __device__ __forceinline__ void add_triangle(d3 a, d3 b, d3 c) {
@@ -43,7 +60,7 @@ struct ExcessAcc {
         const double den = 1.0 + dot(a, b) + dot(b, c) + dot(c, a);
         if (!(den > 0.0)) {          // huge triangle: angle outside (-pi/2, pi/2)
             flush();
-            total += atan2(det, den);
+            total += atan2_general(det, den);
             return;
         }
         const double nre = re * den - im * det;
@@ -289,9 +306,13 @@ __device__ __forceinline__ int crossing_kind(double dp, double dq, bool p_inside
 // Returns -1 (empty) or the 4-bit set of clip edges that cut.
 template <int DIM>
 __device__ __forceinline__ int quad_prepass(const CellsView &gs, int64_t s, const CellsView &gc, int64_t c) {
+    // Cells stored clockwise are NOT reversed: a clockwise clip cell has its interior on the other side
+    // of every edge (the signed distances change sign); a clockwise subject only changes the sign of the
+    // final area.
     double sv[4][DIM], cv[4][DIM];
-    load_quad<DIM>(gs.verts + s * 4 * DIM, gs.flip && gs.flip[s], sv);
-    load_quad<DIM>(gc.verts + c * 4 * DIM, gc.flip && gc.flip[c], cv);
+    load_quad<DIM>(gs.verts + s * 4 * DIM, false, sv);
+    load_quad<DIM>(gc.verts + c * 4 * DIM, false, cv);
+    const bool cflip = gc.flip && gc.flip[c];
     uint32_t cut = 0;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -306,8 +327,9 @@ __device__ __forceinline__ int quad_prepass(const CellsView &gs, int64_t s, cons
         uint32_t me = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const double d = DIM == 3 ? fma(nx, sv[i][0], fma(ny, sv[i][1], nz * sv[i][2]))
-                                      : fma(nx, sv[i][0], fma(ny, sv[i][1], h0));
+            double d = DIM == 3 ? fma(nx, sv[i][0], fma(ny, sv[i][1], nz * sv[i][2]))
+                                : fma(nx, sv[i][0], fma(ny, sv[i][1], h0));
+            if (cflip) d = -d;
             if (d >= 0.0) me |= 1u << i;
         }
         if (me == 0u) return -1;
@@ -323,10 +345,11 @@ __device__ double quad_cut_area(const CellsView &gs, int64_t s, const CellsView 
                                 double *smem /* QUAD_SLOTS * DIM * NT doubles */) {
     PointTable<DIM, NT> tab{smem + threadIdx.x};
     const double *cbase = gc.verts + c * 4 * DIM;
-    const bool cflip = gc.flip && gc.flip[c];
+    const double sc = (gc.flip && gc.flip[c]) ? -1.0 : 1.0;        // clockwise clip cell: normals negated
+    const double ss = (gs.flip && gs.flip[s]) ? -1.0 : 1.0;        // clockwise subject: area negated
     {
         double sv[4][DIM];
-        load_quad<DIM>(gs.verts + s * 4 * DIM, gs.flip && gs.flip[s], sv);
+        load_quad<DIM>(gs.verts + s * 4 * DIM, false, sv);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -337,15 +360,15 @@ __device__ double quad_cut_area(const CellsView &gs, int64_t s, const CellsView 
     while (cut) {
         const int e = __ffs(cut) - 1;
         cut &= cut - 1u;
-        const int iu = cflip ? 3 - e : e, iv = cflip ? 3 - ((e + 1) & 3) : (e + 1) & 3;
+        const int iu = e, iv = (e + 1) & 3;
         double u[3] = {0.0, 0.0, 0.0}, v[3] = {0.0, 0.0, 0.0};
 #pragma unroll
         for (int k = 0; k < DIM; ++k) { u[k] = __ldg(cbase + iu * DIM + k); v[k] = __ldg(cbase + iv * DIM + k); }
         double nx, ny, nz = 0.0, h0 = 0.0;
         if (DIM == 3) {
-            nx = u[1] * v[2] - u[2] * v[1]; ny = u[2] * v[0] - u[0] * v[2]; nz = u[0] * v[1] - u[1] * v[0];
+            nx = sc * (u[1] * v[2] - u[2] * v[1]); ny = sc * (u[2] * v[0] - u[0] * v[2]); nz = sc * (u[0] * v[1] - u[1] * v[0]);
         } else {
-            nx = -(v[1] - u[1]); ny = v[0] - u[0];
+            nx = -sc * (v[1] - u[1]); ny = sc * (v[0] - u[0]);
             h0 = -(nx * u[0] + ny * u[1]);
         }
         auto dist = [&](int id) -> double {
@@ -442,7 +465,7 @@ __device__ double quad_cut_area(const CellsView &gs, int64_t s, const CellsView 
             acc.add_triangle(a, b, cc);
             b = cc;
         }
-        return acc.area();
+        return ss * acc.area();
     } else {
         double sarea = 0.0;
         const double x0 = tab.get(ia, 0), y0 = tab.get(ia, 1);
@@ -454,7 +477,7 @@ __device__ double quad_cut_area(const CellsView &gs, int64_t s, const CellsView 
             sarea += ax * by - ay * bx;
             ax = bx; ay = by;
         }
-        return 0.5 * sarea;
+        return 0.5 * ss * sarea;
     }
 }
 
