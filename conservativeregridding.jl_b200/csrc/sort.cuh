@@ -4,7 +4,8 @@
 // (/root/reference/src/regridder/intersection_areas.jl:115-121).  8-bit digits; per pass:
 //   upsweep   : per-tile digit histogram                         (reads keys: 8 B/elem)
 //   scan      : exclusive scan of the [256][ntiles] table         (scan.cuh)
-//   downsweep : stable rank (warp match + per-warp counters) and scatter
+//   downsweep : stable rank (warp match + per-warp counters), the tile is staged in shared memory in
+//               digit order and written out in contiguous per-digit segments
 //               (reads 16 B/elem, writes 16 B/elem)
 // so one pass moves 40 B/element; HBM-bound.  The sort is stable, which the assembly uses
 // to derive the CSC order from the CSR order with passes over the column bits only.
@@ -41,7 +42,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_downsweep_kernel(
     uint64_t *__restrict__ keys_out, uint64_t *__restrict__ vals_out, int64_t n, int shift, int ntiles,
     const uint32_t *__restrict__ hist_scanned) {
     __shared__ uint32_t whist[RS_WARPS][RS_RADIX];
-    __shared__ uint32_t gbase[RS_RADIX];
+    __shared__ uint32_t gbase[RS_RADIX], dstart[RS_RADIX], scan_tmp[33];
+    __shared__ uint64_t skey[RS_TILE], sval[RS_TILE];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&whist[0][0])[i] = 0;
     __syncthreads();
@@ -73,22 +75,47 @@ __global__ void __launch_bounds__(RS_THREADS) rs_downsweep_kernel(
         __syncwarp();
     }
     __syncthreads();
+    uint32_t dcount;
     {   // digit `threadIdx.x`: exclusive scan of the per-warp counts + global base
         const int d = threadIdx.x;
         uint32_t run = 0;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) { uint32_t c = whist[w][d]; whist[w][d] = run; run += c; }
         gbase[d] = hist_scanned[(size_t)d * ntiles + blockIdx.x];
+        dcount = run;
+    }
+    // where the tile's run of digit d starts inside the tile (exclusive scan over the 256 digits)
+    {
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan<uint32_t>(dcount, scan_tmp, &total);
+        dstart[threadIdx.x] = ex;
     }
     __syncthreads();
+    // stage the tile in shared memory in digit order (stable), ...
 #pragma unroll
     for (int k = 0; k < RS_ITEMS; ++k) {
         int64_t i = base + 32 * k + lane;
         if (i < n) {
             const uint32_t d = (uint32_t)(key[k] >> shift) & 0xFFu;
-            const uint32_t pos = gbase[d] + whist[wid][d] + rank[k];
-            keys_out[pos] = key[k];
-            vals_out[pos] = vals_in[i];
+            const uint32_t lp = dstart[d] + whist[wid][d] + rank[k];
+            skey[lp] = key[k];
+            sval[lp] = vals_in[i];
+        }
+    }
+    __syncthreads();
+    // ... then write it out: consecutive threads hold consecutive elements of a digit's run, so the
+    // scatter goes out in contiguous segments (one per digit present in the tile)
+    const int64_t tile_base = (int64_t)blockIdx.x * RS_TILE;
+    const int tile_n = (int)min((int64_t)RS_TILE, n - tile_base);
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; ++k) {
+        const int j = k * RS_THREADS + threadIdx.x;
+        if (j < tile_n) {
+            const uint64_t kk = skey[j];
+            const uint32_t d = (uint32_t)(kk >> shift) & 0xFFu;
+            const uint32_t pos = gbase[d] + ((uint32_t)j - dstart[d]);
+            keys_out[pos] = kk;
+            vals_out[pos] = sval[j];
         }
     }
 }
