@@ -59,7 +59,10 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs.  One long-running
+    `nvidia-smi -lms` process, started BEFORE the warm-up steps: its start-up (fork + NVML init, which
+    takes driver locks) stalled the first timed build by several milliseconds when it was started at the
+    beginning of the timed region.  Only the rows read inside the timed region are reported."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -72,7 +75,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -81,9 +84,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -93,7 +96,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for (t, r) in self.rows if t0 is None or (t0 <= t <= t1 + 0.05)]
+        if not rows and self.rows:          # region shorter than one polling interval: the closest row
+            rows = [min(self.rows, key=lambda tr: abs(tr[0] - (t1 if t1 is not None else tr[0])))[1]]
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -273,12 +279,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step(False)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
     launches0 = _lib.launch_count()
     barrier()
     t_wall0 = time.perf_counter()
@@ -289,7 +295,7 @@ def main():
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = _lib.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_wall0, t_wall0 + t_wall) if rank == 0 else None
     total_ms = start.elapsed_time(stop)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
