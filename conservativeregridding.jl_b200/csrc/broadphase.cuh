@@ -34,6 +34,7 @@ constexpr int BP_MAX_QUERY = 1 << 18;   // a destination cell covering more bins
 #ifndef BP_QUERY_MINB
 #define BP_QUERY_MINB 10
 #endif
+constexpr int BP_SLAB = 32;             // candidates per destination cell kept by the count pass (slab[k][cell])
 constexpr int BP_SHORT_ROW = 48;        // rows with at most this many candidates are column-sorted by one thread
 constexpr double BP_BIG_ANGLE = 0.2;    // rad; larger spherical cells are "big"
 constexpr double BP_MIN_W = 0.05;       // a face is usable only if all vertices have w > this
@@ -325,7 +326,8 @@ __device__ __forceinline__ int home_face(const double *p, int n) {
 
 // FILL = false: cand_count[d] = number of candidates of destination cell d; big destination
 //               cells (count = n_src) are appended to big_dst; big_dst_counter[1] is set when some
-//               cell has more than BP_SHORT_ROW candidates.
+//               cell has more than BP_SHORT_ROW candidates, big_dst_counter[2] when some cell has more
+//               than BP_SLAB (the first BP_SLAB candidates of every cell are kept in `slab`).
 // FILL = true : pairs[cand_off[d] + k] = (src, d); big destination cells are skipped (filled by
 //               bp_fill_big_dst_kernel).
 template <int DIM, bool FILL>
@@ -336,7 +338,8 @@ __global__ void __launch_bounds__(128, BP_QUERY_MINB) bp_query_kernel(CellsView 
                                                        int64_t n_src, uint32_t *__restrict__ cand_count,
                                                        const int64_t *__restrict__ cand_off,
                                                        int2 *__restrict__ pairs, int32_t *__restrict__ big_dst,
-                                                       uint32_t *__restrict__ big_dst_counter) {
+                                                       uint32_t *__restrict__ big_dst_counter,
+                                                       int32_t *__restrict__ slab) {
     __shared__ CellStage<DIM, 128> stage;
     const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int n;
@@ -360,9 +363,11 @@ __global__ void __launch_bounds__(128, BP_QUERY_MINB) bp_query_kernel(CellsView 
             cand_count[d] = (uint32_t)n_src;
             big_dst[atomicAdd(big_dst_counter, 1u)] = (int32_t)d;
             if (n_src > BP_SHORT_ROW) big_dst_counter[1] = 1u;
+            if (slab) slab[d] = -1;                           // marker: filled by bp_fill_big_dst_kernel
         }
         return;
     }
+    const int64_t nd = g.ncells;
     uint32_t cnt = 0;
     int2 *out = FILL ? pairs + cand_off[d] : nullptr;
     for (int by = b.y0 >> 4; by <= (b.y1 >> 4); ++by)
@@ -377,17 +382,38 @@ __global__ void __launch_bounds__(128, BP_QUERY_MINB) bp_query_kernel(CellsView 
                 // report the pair only in the first bin common to both boxes
                 if ((max(sx0, b.x0) >> 4) != bx || (max(sy0, b.y0) >> 4) != by) continue;
                 if (FILL) out[cnt] = make_int2(e.x, (int)d);
+                else if (slab && cnt < BP_SLAB) slab[(size_t)cnt * nd + d] = e.x;
                 ++cnt;
             }
         }
     for (int k = 0; k < n_big_src; ++k) {
         if (FILL) out[cnt] = make_int2(big_src[k], (int)d);
+        else if (slab && cnt < BP_SLAB) slab[(size_t)cnt * nd + d] = big_src[k];
         ++cnt;
     }
     if (!FILL) {
         cand_count[d] = cnt;
         if (cnt > BP_SHORT_ROW) big_dst_counter[1] = 1u;      // flag: some row is long (benign race, same value)
+        if (cnt > BP_SLAB) big_dst_counter[2] = 1u;           // flag: the slab does not hold every candidate
     }
+}
+
+// The count pass keeps the first BP_SLAB candidates of every destination cell in slab[k][cell]
+// (coalesced across cells); when no cell has more, the pair list is a copy of the slab and the
+// second traversal of the bins is skipped.
+__global__ void __launch_bounds__(256) bp_fill_slab_kernel(const int32_t *__restrict__ slab, int64_t nd,
+                                                           const uint32_t *__restrict__ cand_count,
+                                                           const int64_t *__restrict__ cand_off,
+                                                           int2 *__restrict__ pairs) {
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= nd) return;
+    const uint32_t cnt = cand_count[d];
+    if (cnt == 0) return;
+    const int32_t first = slab[d];
+    if (first < 0) return;                                    // big destination cell
+    int2 *out = pairs + cand_off[d];
+    out[0] = make_int2(first, (int)d);
+    for (uint32_t k = 1; k < cnt; ++k) out[k] = make_int2(slab[(size_t)k * nd + d], (int)d);
 }
 
 __global__ void __launch_bounds__(256) bp_fill_big_dst_kernel(const int32_t *__restrict__ big_dst,

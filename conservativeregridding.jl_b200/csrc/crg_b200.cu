@@ -595,9 +595,12 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     DevBuf<int64_t> cand_off;
     CRG_TRY(cand_count.alloc_tmp((size_t)nd + 1, st));
     CRG_TRY(cand_off.alloc_tmp((size_t)nd + 1, st));
+    DevBuf<int32_t> slab;
+    static const bool allow_slab = !(getenv("CRG_QUERY_SLAB") && atoi(getenv("CRG_QUERY_SLAB")) == 0);
+    if (allow_slab && nd) CRG_TRY(slab.alloc_tmp((size_t)BP_SLAB * nd, st));
     if (nd) bp_query_kernel<DIM, false><<<ceil_div(nd, 128), 128, 0, st>>>(
         gd.view, gd.diam.p, P, bin_start.p, entries.p, big_src.p, n_big_src, ns, cand_count.p, nullptr, nullptr,
-        big_dst.p, counters.p + 1);
+        big_dst.p, counters.p + 1, slab.p);
     if (nd) CRG_LAUNCH_CHECK();
     CRG_TRY((exclusive_scan<uint32_t, int64_t>(cand_count.p, nd, cand_off.p, st)));
     int64_t n_cand = 0;
@@ -614,9 +617,13 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     DevBuf<int2> pairs;
     if (R->opts.keep_candidates) CRG_TRY(pairs.alloc((size_t)n_cand, st));   // outlives the build
     else CRG_TRY(pairs.alloc_tmp((size_t)n_cand, st));
-    if (nd) bp_query_kernel<DIM, true><<<ceil_div(nd, 128), 128, 0, st>>>(
-        gd.view, gd.diam.p, P, bin_start.p, entries.p, big_src.p, n_big_src, ns, nullptr, cand_off.p, pairs.p, nullptr,
-        nullptr);
+    if (nd && slab.p && h_counters[3] == 0) {            // every candidate is in the slab: copy, no second traversal
+        bp_fill_slab_kernel<<<ceil_div(nd, 256), 256, 0, st>>>(slab.p, nd, cand_count.p, cand_off.p, pairs.p);
+    } else if (nd) {
+        bp_query_kernel<DIM, true><<<ceil_div(nd, 128), 128, 0, st>>>(
+            gd.view, gd.diam.p, P, bin_start.p, entries.p, big_src.p, n_big_src, ns, nullptr, cand_off.p, pairs.p, nullptr,
+            nullptr, nullptr);
+    }
     if (nd) CRG_LAUNCH_CHECK();
     if (n_big_dst && ns) {
         dim3 grid((unsigned)std::min<int64_t>(ceil_div(ns, 256), 1024), (unsigned)n_big_dst);
