@@ -534,11 +534,11 @@ def main():
 
 
 # FP64 flops per candidate pair of clip_quad_kernel<3,128> on the cfg5 workload, counted from the SASS page
-# of the ncu capture summarised in profiles/README.md (119.9 DFMA x 2 + 81.1 DMUL + 18.0 DADD per pair;
+# of the ncu capture summarised in profiles/README.md (111.1 DFMA x 2 + 86.5 DMUL + 30.7 DADD per pair;
 # the first, division-based kernel of this round executed 339.6).
-CLIP_FLOPS_PER_PAIR = 338.8
+CLIP_FLOPS_PER_PAIR = 339.4
 # dram__bytes_read.sum + dram__bytes_write.sum of one forward spmv launch on cfg5 (ncu --set full)
-SPMV_TRAFFIC_BYTES = 158312960
+SPMV_TRAFFIC_BYTES = 157804800
 
 if __name__ == "__main__":
     main()
