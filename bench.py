@@ -259,7 +259,7 @@ def main():
         e = [ev() for _ in range(6)] if record else None
         if record: e[0].record()
         factory = lambda rg, cg: _LocalB200(rg, cg, stream=stream)  # noqa: E731
-        S = ShardedRegridder(dst_dev, src_dev, local_factory=factory, device=dev)
+        S = ShardedRegridder(dst_dev, src_dev, local_factory=factory, device=dev, balance=True)
         if record: e[1].record()
         flush.sum()
         if record: e[2].record()
@@ -485,7 +485,7 @@ def main():
             dt = torch.empty((n_dst, 4, 3), dtype=torch.float64, device=dev)
             grid_cells(dst_spec, out=dt)
             factory = lambda rg, cg: _LocalB200(rg, cg, stream=stream)  # noqa: E731
-            S = ShardedRegridder(grids.Grid(dt, dst.manifold), src_spec, local_factory=factory, device=dev)
+            S = ShardedRegridder(grids.Grid(dt, dst.manifold), src_spec, local_factory=factory, device=dev, balance=True)
             xd = xh_t.to(dev, non_blocking=True) if rank == 0 else None
             y_ = S.regrid(xd)
             xb_ = S.regrid(y_, transpose=True)

@@ -39,6 +39,58 @@ def block_bounds(n: int, world: int) -> List[Tuple[int, int]]:
     return out
 
 
+def balanced_bounds(weights, world: int) -> List[Tuple[int, int]]:
+    """Contiguous blocks of ``range(len(weights))`` with near-equal total weight (SURVEY.md section 8e:
+    destination blocks balanced by candidate count).  ``weights``: non-negative numpy array or tensor."""
+    w = torch.as_tensor(weights, dtype=torch.float64).flatten()
+    n = int(w.numel())
+    if world == 1 or n == 0:
+        return block_bounds(n, world)
+    c = torch.cumsum(w, 0)
+    total = float(c[-1])
+    if not total > 0.0:
+        return block_bounds(n, world)
+    targets = torch.arange(1, world, dtype=torch.float64, device=c.device) * (total / world)
+    i = torch.searchsorted(c, targets).clamp_(max=n - 1)          # first cell whose cumulative weight reaches the target
+    below = torch.where(i > 0, c[(i - 1).clamp_(min=0)], torch.zeros_like(targets))
+    cuts = torch.where(c[i] - targets <= targets - below, i + 1, i).cpu().tolist()   # cut on the closer side
+    edges = [0] + [min(max(int(x), 0), n) for x in cuts] + [n]
+    for k in range(1, len(edges)):                    # monotone
+        edges[k] = max(edges[k], edges[k - 1])
+    return [(edges[k], edges[k + 1]) for k in range(world)]
+
+
+def candidate_weights(dst: Grid, src: Grid):
+    """Estimated broad-phase candidates per destination cell, (sqrt(a_dst) + sqrt(a_src))^2 / a_src with
+    flat quad areas (fixed-stride 4-vertex cells only; None otherwise).  On cfg5 an equatorial 0.25 deg
+    cell has ~10 candidates, a polar one ~3.5 -- equal-count latitude bands are 1.7x out of balance."""
+    def flat_areas(g, stride=1):
+        v = g.verts[::stride] if stride > 1 and g.offsets is None else g.verts
+        if g.offsets is not None or not hasattr(v, "shape") or len(v.shape) != 3 or v.shape[1] != 4:
+            return None
+        v = torch.as_tensor(v)
+        d1, d2 = v[:, 2] - v[:, 0], v[:, 3] - v[:, 1]
+        if v.shape[2] == 3:
+            return 0.5 * torch.linalg.cross(d1, d2).norm(dim=1)
+        return 0.5 * (d1[:, 0] * d2[:, 1] - d1[:, 1] * d2[:, 0]).abs()
+    if not isinstance(dst, Grid):
+        return None
+    ad = flat_areas(dst)
+    if ad is None:
+        return None
+    if isinstance(src, Grid):
+        a_s = flat_areas(src, max(1, src.ncells // 16384))       # the mean of a sample is enough
+        if a_s is None or a_s.numel() == 0:
+            return None
+        a_s = float(a_s.mean())
+    else:                                             # described grid: mean cell area of a global grid
+        n_src = src.ncells
+        a_s = 4.0 * np.pi * float(getattr(src, "radius", 1.0)) ** 2 / max(n_src, 1)
+    if not a_s > 0.0:
+        return None
+    return (ad.sqrt() + a_s ** 0.5) ** 2 / a_s
+
+
 class _LocalB200:
     """Row-block operator backed by the CUDA engine (one ``crg_regridder`` handle)."""
 
@@ -87,10 +139,12 @@ class ShardedRegridder:
 
     ``local_factory(rows_grid, cols_grid) -> op`` builds the rank-local row-block operator (see
     :class:`_LocalB200` for the protocol); the default is the CUDA engine.  (The CPU tests inject a
-    numpy/scipy factory to exercise the sharding and the collectives under gloo.)"""
+    numpy/scipy factory to exercise the sharding and the collectives under gloo.)
+    ``balance``: False = equal cell counts per block; True = blocks of equal estimated candidate count
+    (:func:`candidate_weights`); an array = per-destination-cell weights.  Collective when not False."""
 
     def __init__(self, dst: Grid, src: Grid, group=None, local_factory: Optional[Callable] = None,
-                 device: Optional[torch.device] = None, normalize: bool = False):
+                 device: Optional[torch.device] = None, normalize: bool = False, balance=False):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -98,6 +152,17 @@ class ShardedRegridder:
         self.device = device if device is not None else torch.device("cpu")
         factory = local_factory or _LocalB200
         self.dst_bounds = block_bounds(self.n_dst, self.world)
+        if balance and self.world > 1:
+            # blocks of near-equal estimated work; rank 0 decides, everybody follows (bit-identical bounds)
+            edges = torch.zeros(self.world + 1, dtype=torch.int64, device=self.device)
+            if self.rank == 0:
+                w = balance if not isinstance(balance, bool) else candidate_weights(dst, src)
+                b = balanced_bounds(w, self.world) if w is not None else self.dst_bounds
+                edges = torch.tensor([b[0][0]] + [hi for _, hi in b], dtype=torch.int64, device=self.device)
+            dist.broadcast(edges, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0,
+                           group=self.group)
+            e = edges.cpu().tolist()
+            self.dst_bounds = [(int(e[k]), int(e[k + 1])) for k in range(self.world)]
         lo, hi = self.dst_bounds[self.rank]
         self.local = factory(dst.slice(lo, hi), src)
         if normalize:

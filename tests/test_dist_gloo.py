@@ -81,6 +81,17 @@ def _worker(rank, world, port, q):
         lo, hi = block_bounds(dst.ncells, world)[rank]
         yl = S.regrid(torch.from_numpy(x0), broadcast=False, gather=False)
         assert yl.shape[0] == hi - lo and np.allclose(yl.numpy(), full.regrid(x0)[lo:hi], rtol=1e-13)
+        # blocks balanced by estimated candidate count (rank 0 decides, bounds broadcast): same results
+        Sb = ShardedRegridder(dst, src, local_factory=_OracleLocal, balance=True)
+        assert Sb.dst_bounds[0][0] == 0 and Sb.dst_bounds[-1][1] == dst.ncells
+        assert all(a[1] == b[0] for a, b in zip(Sb.dst_bounds[:-1], Sb.dst_bounds[1:]))
+        if world == 3:                                         # (two blocks of a symmetric grid are balanced already)
+            assert Sb.dst_bounds != S.dst_bounds             # polar rows are cheaper than equatorial ones
+        assert np.allclose(Sb.dst_areas.numpy(), full.dst_areas, rtol=1e-15)
+        yb = Sb.regrid(torch.from_numpy(x0), broadcast=False)
+        assert np.allclose(yb.numpy(), full.regrid(x0), rtol=1e-13)
+        xbb = Sb.regrid(yb, transpose=True)
+        assert np.allclose(xbb.numpy(), xb.numpy(), rtol=1e-12)
         # normalize!(R): every block scaled by the global maximum(A) (one scalar all-reduce)
         Sn = ShardedRegridder(dst, src, local_factory=_OracleLocal, normalize=True)
         m = full.tocsc().max()

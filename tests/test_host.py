@@ -111,3 +111,18 @@ def test_dims_validation_errors():
         regrid_([0.0] * 9, R, np.ones(4))
     T = transpose(R)
     assert T.shape == (4, 9) and T.src_areas is R.dst_areas and T.dst_temp is R.src_temp
+
+
+def test_balanced_bounds_and_candidate_weights():
+    from crg_b200.dist import balanced_bounds, block_bounds, candidate_weights
+    w = np.array([1.0] * 10 + [3.0] * 10)
+    b = balanced_bounds(w, 2)
+    assert b[0][0] == 0 and b[-1][1] == 20 and b[0][1] == b[1][0]
+    assert abs(w[b[0][0]:b[0][1]].sum() - w[b[1][0]:b[1][1]].sum()) <= 3.0
+    assert balanced_bounds(np.zeros(7), 3) == block_bounds(7, 3)          # degenerate weights: equal counts
+    assert balanced_bounds(np.ones(5), 1) == [(0, 5)]
+    assert [hi - lo for lo, hi in balanced_bounds(np.ones(12), 4)] == [3, 3, 3, 3]
+    dst, src = grids.lonlat_grid(36, 18), grids.healpix_grid(4, "ring")
+    cw = candidate_weights(dst, src).numpy().reshape(18, 36)
+    assert cw[9, 0] > 1.5 * cw[0, 0]                                       # equatorial cells have more candidates
+    assert candidate_weights(grids.polygons_grid([np.array([[0, 0], [1, 0], [0, 1.0]])]), src) is None
