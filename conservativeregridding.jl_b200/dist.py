@@ -141,10 +141,12 @@ class ShardedRegridder:
     :class:`_LocalB200` for the protocol); the default is the CUDA engine.  (The CPU tests inject a
     numpy/scipy factory to exercise the sharding and the collectives under gloo.)
     ``balance``: False = equal cell counts per block; True = blocks of equal estimated candidate count
-    (:func:`candidate_weights`); an array = per-destination-cell weights.  Collective when not False."""
+    (:func:`candidate_weights`); an array = per-destination-cell weights.  Collective when not False.
+    ``bounds``: explicit blocks (identical on every rank), e.g. ``dst_bounds`` of an earlier regridder."""
 
     def __init__(self, dst: Grid, src: Grid, group=None, local_factory: Optional[Callable] = None,
-                 device: Optional[torch.device] = None, normalize: bool = False, balance=False):
+                 device: Optional[torch.device] = None, normalize: bool = False, balance=False,
+                 bounds: Optional[List[Tuple[int, int]]] = None):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -152,7 +154,10 @@ class ShardedRegridder:
         self.device = device if device is not None else torch.device("cpu")
         factory = local_factory or _LocalB200
         self.dst_bounds = block_bounds(self.n_dst, self.world)
-        if balance and self.world > 1:
+        if bounds is not None:                            # e.g. the dst_bounds of an earlier balanced regridder
+            assert len(bounds) == self.world and bounds[0][0] == 0 and bounds[-1][1] == self.n_dst
+            self.dst_bounds = [(int(lo), int(hi)) for lo, hi in bounds]
+        elif balance and self.world > 1:
             # blocks of near-equal estimated work; rank 0 decides, everybody follows (bit-identical bounds)
             edges = torch.zeros(self.world + 1, dtype=torch.int64, device=self.device)
             if self.rank == 0:
