@@ -4,8 +4,9 @@
 // (/root/reference/src/regridder/regridder.jl:87-103): GO.intersection with
 // ConvexConvexSutherlandHodgman (great-circle half-space cuts) followed by GO.area, and per
 // cell GO.area (regridder.jl:165-178).  The arithmetic itself lives in GeometryOps.jl (not
-// in the reference tree); this is the published algorithm, written for one thread per pair
-// with the working polygon ping-ponged through shared memory.
+// in the reference tree); this is the published algorithm in two device forms: clip_pair_area
+// (any convex rings, working polygon ping-ponged through shared memory) and quad_prepass /
+// quad_cut_area (quadrilaterals: symbolic polygon over a per-thread point table).
 #pragma once
 #include "common.cuh"
 

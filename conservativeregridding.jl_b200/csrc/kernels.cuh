@@ -1,5 +1,6 @@
-// kernels.cuh -- clip/area kernel, cell areas, COO -> CSR/CSC assembly helpers, normalize,
-// and the CSR SpMM apply kernels (area division fused in).  The SpMV lives in sell.cuh.
+// kernels.cuh -- clip/area kernels, COO -> CSR/CSC assembly helpers, normalize, and the CSR SpMM
+// apply kernels (area division fused in).  The SpMV lives in sell.cuh, the cell areas in
+// broadphase.cuh (fused into the bounds pass).
 #pragma once
 #include "common.cuh"
 #include "geom.cuh"
@@ -8,21 +9,21 @@
 namespace crg {
 
 // =======================================================================================
-// K3: one thread per candidate pair -> clip + area.  Replaces compute_intersection_areas
-// (/root/reference/src/regridder/intersection_areas.jl:4-32).  FP64-pipe bound.
+// K3: clip + area of every candidate pair.  Replaces compute_intersection_areas
+// (/root/reference/src/regridder/intersection_areas.jl:4-32).  FP64-pipe / issue bound.
 //
-// The kernel has no CTA-wide synchronisation: every thread writes its area to a dense array
-// (0 when the pair does not survive `area > threshold`) and every warp adds its survivor count to
-// the counter of its 1024-pair tile.  A streaming pass (compact_pairs_kernel, after a scan of the
-// tile counters) then compacts the survivors IN ORDER.  Because the candidate list is grouped by
-// destination cell in increasing order, the compacted COO triples are sorted by row, and the
-// assembly needs radix passes over the column bits and the row bits only once each (6 passes
-// instead of 9).  (A single-pass chained-scan compaction inside this kernel was measured 40 %
-// slower: tiles with long clips hold back the retirement of their successors.)
+// Neither kernel has CTA-wide synchronisation: every pair's area goes to a dense array (0 when the
+// pair does not survive `area > threshold`) and the survivor counts are added to the counter of the
+// pair's 1024-pair tile.  A streaming pass (compact_pairs_kernel, after a scan of the tile counters)
+// then compacts the survivors IN ORDER.  Because the candidate list is grouped by destination cell
+// in increasing order, the compacted COO triples are grouped by row, which is what the assembly
+// builds on (crg_b200.cu: assemble).  (A single-pass chained-scan compaction inside the clip kernel
+// was measured 40 % slower: tiles with long clips hold back the retirement of their successors.)
 // =======================================================================================
 constexpr int CLIP_TILE = 1024;      // pairs per compaction tile
 
-// QUAD = true: both cells are quadrilaterals stored with a fixed stride (fast path).
+// General cells (ragged rings, triangles, up to CRG_MAX_VERTS vertices): one thread per pair,
+// Sutherland-Hodgman ping-ponged through two shared-memory polygons (geom.cuh: clip_pair_area).
 template <int DIM, int NT, int MAXW>
 __global__ void __launch_bounds__(NT) clip_kernel(CellsView gd, CellsView gs, const int2 *__restrict__ pairs,
                                                   int64_t npairs, double thresh, double *__restrict__ area_out,
