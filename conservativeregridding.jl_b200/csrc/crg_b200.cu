@@ -342,7 +342,7 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
             R->has_At = true;
         }
         R->stats.sort_passes_csc = p1;
-        *t_sort_csr1 = (int)tm.ev.size();     // (phase names: "sort_csr" = column passes + CSC, "sort_csc" = row passes + CSR)
+        *t_sort_csr1 = (int)tm.ev.size();     // (long-row path only: here phase "sort_csr" = column passes + A^T, "sort_csc" = row passes + A)
         CRG_TRY(tm.mark());
         // (row, col) order
         CRG_TRY(radix_sort_pairs(ka, va, kb, vb, n, 32, 32 + bits_dst, &inb, &p2, st));

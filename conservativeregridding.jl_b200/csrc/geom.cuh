@@ -226,13 +226,8 @@ __device__ double clip_pair_area(const CellsView &gs, int64_t s, const CellsView
 
 
 // ------------------------------------------------------------------------------------
-// Fast path: quadrilateral x quadrilateral (every structured grid of BASELINE.json).
-//   * the clip cell lives in registers (edge loop fully unrolled, static indexing),
-//   * the working polygon is clipped IN PLACE in one shared-memory buffer of 8 slots: an
-//     output vertex can land at most one slot ahead of the next input vertex (two with
-//     round-off-induced double crossings), so the next two input vertices are carried in
-//     registers -- half the shared memory of the ping-pong version, twice the occupancy,
-//   * cells are fetched with 16-byte loads.
+// Fast path: quadrilateral x quadrilateral (every structured grid of BASELINE.json): quad_prepass +
+// quad_cut_area below, driven by clip_quad_kernel (kernels.cuh).  Cells are fetched with 16-byte loads.
 // ------------------------------------------------------------------------------------
 template <int DIM>
 __device__ __forceinline__ void load_quad(const double *__restrict__ p, bool flip, double (&v)[4][DIM]) {
