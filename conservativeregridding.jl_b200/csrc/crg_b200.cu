@@ -219,37 +219,66 @@ static int fill_csr(Csr &M, const uint64_t *keys, const double *vals, int64_t nn
     return CRG_OK;
 }
 
-// CSR -> SELL-32-sigma (sell.cuh): window sort, slice offsets, piece list, scatter.
-static int build_sell(Csr &M, cudaStream_t st) {
+// CSR -> SELL-32-sigma (sell.cuh): window sort, slice offsets, piece list, scatter -- in two halves
+// around the one host round trip (the padded size), so that two matrices on two streams can both be
+// enqueued before the host waits for either.
+static uint32_t *g_host_scratch[64];       // small pinned staging area per device (8 slots of 4 words)
+static int host_scratch(int dev, int slot, uint32_t **out) {
+    if (dev < 0 || dev >= 64) return set_error(CRG_ERR_INVALID, "device ordinal %d not supported", dev);
+    if (!g_host_scratch[dev]) {
+        uint32_t *p = nullptr;
+        CRG_CUDA(cudaHostAlloc((void **)&p, 8 * 4 * sizeof(uint32_t), cudaHostAllocDefault));
+        uint32_t *expected = nullptr;
+        if (!__atomic_compare_exchange_n(&g_host_scratch[dev], &expected, p, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE))
+            cudaFreeHost(p);
+    }
+    *out = g_host_scratch[dev] + 4 * slot;
+    return CRG_OK;
+}
+
+struct SellCtx {
+    DevBuf<int32_t> steps;
+    DevBuf<uint32_t> cnt, off;     // [0, nslices]: extra pieces, (nslices, 2 nslices]: partial slots
+    uint32_t *h = nullptr;         // pinned: total steps, extra pieces, partial slots
+    int nslices = 0;
+    int64_t npos = 0;
+};
+
+static int sell_pre(Csr &M, cudaStream_t st, SellCtx &c, int device, int slot) {
     M.sell_npieces = 0;
     M.sell_padded = 0;
     if (M.n_rows == 0) return CRG_OK;
     const int nwin = (int)((M.n_rows + SELL_SIGMA - 1) / SELL_SIGMA);
-    const int64_t npos = (int64_t)nwin * SELL_SIGMA;
-    const int nslices = (int)(npos / 32);
-    DevBuf<int32_t> steps;
+    c.npos = (int64_t)nwin * SELL_SIGMA;
+    c.nslices = (int)(c.npos / 32);
+    const int nslices = c.nslices;
     M.sell_nslices = nslices;
-    DevBuf<uint32_t> cnt, off;     // [0, nslices]: extra pieces, (nslices, 2 nslices]: partial slots
-    CRG_TRY(M.sell_perm.alloc((size_t)npos, st));
-    CRG_TRY(M.sell_rlen.alloc((size_t)npos, st));
+    CRG_TRY(host_scratch(device, slot, &c.h));
+    CRG_TRY(M.sell_perm.alloc((size_t)c.npos, st));
+    CRG_TRY(M.sell_rlen.alloc((size_t)c.npos, st));
     CRG_TRY(M.sell_slice_off.alloc((size_t)nslices + 1, st));
-    CRG_TRY(steps.alloc_tmp((size_t)nslices, st));
-    CRG_TRY(cnt.alloc_tmp((size_t)2 * nslices, st));
-    CRG_TRY(off.alloc_tmp((size_t)2 * nslices + 2, st));
-    sell_sort_kernel<<<nwin, SELL_SIGMA, 0, st>>>(M.rowptr.p, M.n_rows, M.sell_perm.p, M.sell_rlen.p, steps.p);
+    CRG_TRY(c.steps.alloc_tmp((size_t)nslices, st));
+    CRG_TRY(c.cnt.alloc_tmp((size_t)2 * nslices, st));
+    CRG_TRY(c.off.alloc_tmp((size_t)2 * nslices + 2, st));
+    sell_sort_kernel<<<nwin, SELL_SIGMA, 0, st>>>(M.rowptr.p, M.n_rows, M.sell_perm.p, M.sell_rlen.p, c.steps.p);
     CRG_LAUNCH_CHECK();
-    CRG_TRY((exclusive_scan<int32_t, int32_t>(steps.p, nslices, M.sell_slice_off.p, st)));
-    sell_count_kernel<<<ceil_div(nslices, 256), 256, 0, st>>>(steps.p, nslices, cnt.p, cnt.p + nslices);
+    CRG_TRY((exclusive_scan<int32_t, int32_t>(c.steps.p, nslices, M.sell_slice_off.p, st)));
+    sell_count_kernel<<<ceil_div(nslices, 256), 256, 0, st>>>(c.steps.p, nslices, c.cnt.p, c.cnt.p + nslices);
     CRG_LAUNCH_CHECK();
-    CRG_TRY((exclusive_scan<uint32_t, uint32_t>(cnt.p, nslices, off.p, st)));
+    CRG_TRY((exclusive_scan<uint32_t, uint32_t>(c.cnt.p, nslices, c.off.p, st)));
     CRG_TRY(M.sell_cut_base.alloc((size_t)nslices + 1, st));
-    CRG_TRY((exclusive_scan<uint32_t, uint32_t>(cnt.p + nslices, nslices, M.sell_cut_base.p, st)));
-    int32_t total_steps = 0;
-    uint32_t np = 0, nslots = 0;
-    CRG_CUDA(cudaMemcpyAsync(&total_steps, M.sell_slice_off.p + nslices, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CRG_CUDA(cudaMemcpyAsync(&np, off.p + nslices, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CRG_CUDA(cudaMemcpyAsync(&nslots, M.sell_cut_base.p + nslices, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CRG_CUDA(cudaStreamSynchronize(st));
+    CRG_TRY((exclusive_scan<uint32_t, uint32_t>(c.cnt.p + nslices, nslices, M.sell_cut_base.p, st)));
+    CRG_CUDA(cudaMemcpyAsync(c.h + 0, M.sell_slice_off.p + nslices, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CRG_CUDA(cudaMemcpyAsync(c.h + 1, c.off.p + nslices, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CRG_CUDA(cudaMemcpyAsync(c.h + 2, M.sell_cut_base.p + nslices, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    return CRG_OK;
+}
+
+// (after the stream of sell_pre has been synchronised)
+static int sell_post(Csr &M, cudaStream_t st, SellCtx &c) {
+    if (M.n_rows == 0) return CRG_OK;
+    const int32_t total_steps = (int32_t)c.h[0];
+    const uint32_t np = c.h[1], nslots = c.h[2];
     M.sell_npieces = (int)np;
     M.sell_padded = (int64_t)total_steps * 32;
     CRG_TRY(M.sell_vals.alloc((size_t)M.sell_padded, st));
@@ -258,15 +287,22 @@ static int build_sell(Csr &M, cudaStream_t st) {
     CRG_TRY(M.sell_partial.alloc((size_t)nslots * 32, st));
     CRG_TRY(M.sell_ticket.alloc((size_t)nslots, st));
     CRG_CUDA(cudaMemsetAsync(M.sell_ticket.p, 0, sizeof(unsigned int) * (size_t)(nslots > 0 ? nslots : 1), st));
-    sell_pieces_kernel<<<ceil_div(nslices, 256), 256, 0, st>>>(steps.p, nslices, off.p, M.sell_cut_base.p, M.sell_pieces.p);
+    sell_pieces_kernel<<<ceil_div(c.nslices, 256), 256, 0, st>>>(c.steps.p, c.nslices, c.off.p, M.sell_cut_base.p, M.sell_pieces.p);
     CRG_LAUNCH_CHECK();
-    sell_fill_kernel<<<ceil_div(npos, 256), 256, 0, st>>>(M.rowptr.p, M.colidx.p, M.vals.p, M.sell_perm.p, M.sell_slice_off.p,
-                                                          npos, M.sell_vals.p, M.sell_cols.p);
+    sell_fill_kernel<<<ceil_div(c.npos, 256), 256, 0, st>>>(M.rowptr.p, M.colidx.p, M.vals.p, M.sell_perm.p, M.sell_slice_off.p,
+                                                            c.npos, M.sell_vals.p, M.sell_cols.p);
     CRG_LAUNCH_CHECK();
     return CRG_OK;
 }
 
-static int finish_csr(Csr &M, cudaStream_t st) { return build_sell(M, st); }
+static int build_sell(Csr &M, cudaStream_t st, int device) {
+    SellCtx c;
+    CRG_TRY(sell_pre(M, st, c, device, 0));
+    CRG_CUDA(cudaStreamSynchronize(st));
+    return sell_post(M, st, c);
+}
+
+static int finish_csr(Csr &M, cudaStream_t st, int device) { return build_sell(M, st, device); }
 
 // Sort COO (keys = row<<32|col, f64 values) -> CSR; optionally also the transposed CSR.
 // keys/vals buffers have capacity `cap` (>= n) and are consumed.
@@ -278,7 +314,7 @@ static int finish_csr(Csr &M, cudaStream_t st) { return build_sell(M, st); }
 //   row_sorted_unique = false (crg_build_from_coo: arbitrary order, duplicates): full-key sort,
 //     segmented duplicate sum, then the column-bit passes for the transpose.
 static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &valA, int64_t n, bool row_sorted_unique,
-                    bool short_rows, Timer &tm, int *t_sort_csr0, int *t_sort_csr1, int *t_sort_csc1) {
+                    bool short_rows, cudaStream_t s2, Timer &tm, int *t_sort_csr0, int *t_sort_csr1, int *t_sort_csc1) {
     cudaStream_t st = R->stream;
     const int bits_src = ilog2_ceil((uint64_t)(R->n_src > 1 ? R->n_src : 2));
     const int bits_dst = ilog2_ceil((uint64_t)(R->n_dst > 1 ? R->n_dst : 2));
@@ -299,32 +335,77 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
     if (n >= ((int64_t)1 << 31)) return set_error(CRG_ERR_NOMEM, "nnz=%lld exceeds int32 indexing", (long long)n);
 
     if (row_sorted_unique && short_rows) {
-        // every row is a few entries long: CSR(A) straight from the row-grouped triples (one thread
-        // sorts a row by column), then the column-bit passes alone give the (col, row) order.
+        // Every row is a few entries long: CSR(A) comes straight from the row-grouped triples (one thread
+        // sorts a row by column); the stable column-bit passes over the same triples give the (col, row)
+        // order for A^T.  The two only READ the triples, so the A side runs on the side stream while the
+        // radix passes of the A^T side run on the main stream (the passes ping-pong between two scratch
+        // pairs and never write the input).
         R->nnz = nnz;
-        CRG_TRY(alloc_csr(A, R->n_dst, R->n_src, nnz, st));
+        const bool fork = R->opts.build_transpose && nnz > 0 && s2 != st;
+        cudaStream_t sa = fork ? s2 : st;                 // stream of the A side
+        cudaEvent_t ev_in = nullptr, ev_a0 = nullptr, ev_a1 = nullptr;
+        CRG_CUDA(cudaEventCreate(&ev_a0));
+        CRG_CUDA(cudaEventCreate(&ev_a1));
+        struct EvGuard { cudaEvent_t *e[3]; ~EvGuard() { for (auto p : e) if (*p) cudaEventDestroy(*p); } } evg{{&ev_in, &ev_a0, &ev_a1}};
+        uint64_t *kt = ka, *vt = va;                      // where the (col, row)-ordered triples end up
+        if (fork) {
+            CRG_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+            CRG_CUDA(cudaEventRecord(ev_in, st));
+            CRG_CUDA(cudaStreamWaitEvent(sa, ev_in, 0));
+        }
+        DevBuf<uint64_t> keyC;
+        DevBuf<double> valC;
+        if (R->opts.build_transpose && nnz > 0) {
+            // first pass a -> b, the others between b and c
+            const int first_hi = bits_src < 8 ? bits_src : 8;
+            int q1 = 0, q2 = 0;
+            bool in_second = false;
+            CRG_TRY(radix_sort_pairs(ka, va, kb, vb, n, 0, first_hi, &inb, &q1, st));
+            kt = inb ? kb : ka; vt = inb ? vb : va;
+            if (bits_src > 8) {
+                CRG_TRY(keyC.alloc_tmp((size_t)n, st));
+                CRG_TRY(valC.alloc_tmp((size_t)n, st));
+                // (n <= 1: no pass runs and the triples stay where they are)
+                CRG_TRY(radix_sort_pairs(kt, vt, keyC.p, (uint64_t *)valC.p, n, 8, bits_src, &in_second, &q2, st));
+                if (in_second) { kt = keyC.p; vt = (uint64_t *)valC.p; }
+            }
+            p1 = q1 + q2;
+        }
+        // ---- A side --------------------------------------------------------------------------------
+        CRG_CUDA(cudaEventRecord(ev_a0, sa));
+        CRG_TRY(alloc_csr(A, R->n_dst, R->n_src, nnz, sa));
         if (nnz > 0) {
-            CRG_TRY(fill_csr(A, ka, nullptr, nnz, false, false, st));
-            row_sort_split_kernel<<<ceil_div(A.n_rows, ROWSORT_ROWS), ROWSORT_ROWS, 0, st>>>(ka, (double *)va, A.rowptr.p, A.n_rows, A.colidx.p, A.vals.p);
+            CRG_TRY(fill_csr(A, ka, nullptr, nnz, false, false, sa));
+            row_sort_split_kernel<<<ceil_div(A.n_rows, ROWSORT_ROWS), ROWSORT_ROWS, 0, sa>>>(ka, (const double *)va, A.rowptr.p, A.n_rows, A.colidx.p, A.vals.p);
             CRG_LAUNCH_CHECK();
         }
-        CRG_TRY(finish_csr(A, st));
+        SellCtx ca, ct;
+        CRG_TRY(sell_pre(A, sa, ca, R->device, 0));
         R->stats.sort_passes_csr = 0;
-        *t_sort_csr1 = (int)tm.ev.size();
-        CRG_TRY(tm.mark());
+        // ---- A^T side, after the passes ----------------------------------------------------------------
         if (R->opts.build_transpose) {
-            CRG_TRY(radix_sort_pairs(ka, va, kb, vb, n, 0, bits_src, &inb, &p1, st));
-            if (inb) { std::swap(ka, kb); std::swap(va, vb); }
             CRG_TRY(alloc_csr(T, R->n_src, R->n_dst, nnz, st));
-            if (nnz > 0) {
-                CRG_TRY(fill_csr(T, ka, (const double *)va, nnz, true, true, st));      // (col, row) order: rows of A^T = low word
-            }
-            CRG_TRY(finish_csr(T, st));
+            if (nnz > 0) CRG_TRY(fill_csr(T, kt, (const double *)vt, nnz, true, true, st));      // (col, row) order: rows of A^T = low word
+            CRG_TRY(sell_pre(T, st, ct, R->device, 1));
+        }
+        // both matrices are enqueued up to their one host round trip: wait, then the second halves
+        CRG_CUDA(cudaStreamSynchronize(sa));
+        CRG_TRY(sell_post(A, sa, ca));
+        CRG_CUDA(cudaEventRecord(ev_a1, sa));
+        if (R->opts.build_transpose) {
+            CRG_CUDA(cudaStreamSynchronize(st));
+            CRG_TRY(sell_post(T, st, ct));
             R->has_At = true;
         }
         R->stats.sort_passes_csc = p1;
+        if (fork) CRG_CUDA(cudaStreamWaitEvent(st, ev_a1, 0));          // join
+        *t_sort_csr1 = -1;                                // the A side is timed by its own events (it overlaps)
         *t_sort_csc1 = (int)tm.ev.size();
         CRG_TRY(tm.mark());
+        CRG_CUDA(cudaEventSynchronize(ev_a1));
+        float fa = 0.f;
+        if (cudaEventElapsedTime(&fa, ev_a0, ev_a1) != cudaSuccess) cudaGetLastError();
+        R->stats.ms_sort_csr = fa;
         return CRG_OK;
     }
 
@@ -338,7 +419,7 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
             if (nnz > 0) {
                 CRG_TRY(fill_csr(T, ka, (const double *)va, nnz, true, true, st));      // (col, row) order: rows of A^T = low word
             }
-            CRG_TRY(finish_csr(T, st));
+            CRG_TRY(finish_csr(T, st, R->device));
             R->has_At = true;
         }
         R->stats.sort_passes_csc = p1;
@@ -352,7 +433,7 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
         if (nnz > 0) {
             CRG_TRY(fill_csr(A, ka, (const double *)va, nnz, false, true, st));
         }
-        CRG_TRY(finish_csr(A, st));
+        CRG_TRY(finish_csr(A, st, R->device));
         *t_sort_csc1 = (int)tm.ev.size();
         CRG_TRY(tm.mark());
         return CRG_OK;
@@ -386,7 +467,7 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
     if (nnz > 0) {
         CRG_TRY(fill_csr(A, ka, (const double *)va, nnz, false, true, st));
     }
-    CRG_TRY(finish_csr(A, st));
+    CRG_TRY(finish_csr(A, st, R->device));
     *t_sort_csr1 = (int)tm.ev.size();
     CRG_TRY(tm.mark());
     if (R->opts.build_transpose) {   // swap the key halves and (stably) sort by the new high word only
@@ -398,7 +479,7 @@ static int assemble(crg_regridder *R, DevBuf<uint64_t> &keyA, DevBuf<double> &va
             if (inb) { std::swap(ka, kb); std::swap(va, vb); }
             CRG_TRY(fill_csr(T, ka, (const double *)va, nnz, false, true, st));
         }
-        CRG_TRY(finish_csr(T, st));
+        CRG_TRY(finish_csr(T, st, R->device));
         R->stats.sort_passes_csc = p3;
         R->has_At = true;
     }
@@ -439,6 +520,8 @@ static int do_normalize(crg_regridder *R) {
     CRG_TRY(device_maximum(R));
     return divide_by_scratch(R);
 }
+
+static int device_side_stream(int dev, cudaStream_t *out);
 
 template <int DIM>
 static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *src) {
@@ -692,7 +775,10 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
 
     // ---- K5: assembly ------------------------------------------------------------------------------
     int t0 = 0, t1 = 0, t2 = 0;
-    CRG_TRY(assemble(R, coo_key, coo_val, (int64_t)h_keep, true, short_rows, tm, &t0, &t1, &t2));
+    cudaStream_t side_stream = st;
+    static const bool two_streams = !(getenv("CRG_TWO_STREAMS") && atoi(getenv("CRG_TWO_STREAMS")) == 0);
+    if (two_streams) CRG_TRY(device_side_stream(R->device, &side_stream));
+    CRG_TRY(assemble(R, coo_key, coo_val, (int64_t)h_keep, true, short_rows, side_stream, tm, &t0, &t1, &t2));
     coo_key.release(); coo_val.release();
 
     // ---- K6: normalize ------------------------------------------------------------------------------
@@ -706,8 +792,8 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     S.ms_bin = tm.ms(2, 3);
     S.ms_query = tm.ms(3, 4);
     S.ms_clip = tm.ms(4, 5);
-    S.ms_sort_csr = tm.ms(t0, t1);
-    S.ms_sort_csc = tm.ms(t1, t2);
+    if (t1 >= 0) { S.ms_sort_csr = tm.ms(t0, t1); S.ms_sort_csc = tm.ms(t1, t2); }
+    else S.ms_sort_csc = tm.ms(t0, t2);      // short-row path: the A side (ms_sort_csr, own events) runs inside this span
     S.ms_finish = tm.ms(t2, last);
     S.ms_device = tm.ms(0, last);
     S.ms_total = now_ms() - t_begin;
@@ -732,6 +818,21 @@ static int device_stream(int dev, cudaStream_t *out) {
 }
 
 // Per-device build arena + the mutex that serialises builds on one device.
+// ... and one side stream per device: the assembly builds CSR(A) on it while the radix passes of A^T run
+static cudaStream_t g_dev_stream2[64];
+static int device_side_stream(int dev, cudaStream_t *out) {
+    if (dev < 0 || dev >= 64) return set_error(CRG_ERR_INVALID, "device ordinal %d not supported", dev);
+    if (!g_dev_stream2[dev]) {
+        cudaStream_t s;
+        CRG_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        cudaStream_t expected = nullptr;
+        if (!__atomic_compare_exchange_n(&g_dev_stream2[dev], &expected, s, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE))
+            cudaStreamDestroy(s);
+    }
+    *out = g_dev_stream2[dev];
+    return CRG_OK;
+}
+
 static Arena g_arena[64];
 static std::mutex g_build_mutex[64];
 
@@ -1145,7 +1246,7 @@ int crg_build_from_coo(const crg_options *opts, int64_t n_dst, int64_t n_src, in
         else CRG_CUDA(cudaMemsetAsync(R->src_areas.p, 0, sizeof(double) * (size_t)(n_src > 0 ? n_src : 1), st));
         CRG_TRY(tm.mark());
         int a = 0, b = 0, c = 0;
-        CRG_TRY(assemble(R, keys, vals, nnz, false, false, tm, &a, &b, &c));
+        CRG_TRY(assemble(R, keys, vals, nnz, false, false, R->stream, tm, &a, &b, &c));
         if (R->opts.normalize) CRG_TRY(do_normalize(R));
         CRG_TRY(tm.mark());
         CRG_CUDA(cudaStreamSynchronize(st));

@@ -203,52 +203,46 @@ __global__ void __launch_bounds__(256) rowptr_kernel(const uint64_t *__restrict_
 // Row-grouped COO with short rows -> CSR: a block stages the entries of its ROWSORT_ROWS rows in
 // shared memory (coalesced), one thread per row sorts its entries by column (insertion sort; the
 // candidate lists are a few entries long), and the block writes the CSR column/value arrays, coalesced.
-// A block whose rows hold more than ROWSORT_CAP entries sorts in place in global memory.
+// A block whose rows hold more than ROWSORT_CAP entries sorts inside the CSR arrays (global memory).
 constexpr int ROWSORT_ROWS = 128;
 constexpr int ROWSORT_CAP = 2560;
-__global__ void __launch_bounds__(ROWSORT_ROWS) row_sort_split_kernel(uint64_t *__restrict__ keys, double *__restrict__ vals,
+__global__ void __launch_bounds__(ROWSORT_ROWS) row_sort_split_kernel(const uint64_t *__restrict__ keys,
+                                                                      const double *__restrict__ vals,
                                                                       const int32_t *__restrict__ rowptr, int64_t n_rows,
                                                                       int32_t *__restrict__ colidx,
                                                                       double *__restrict__ out_vals) {
-    __shared__ uint64_t sk[ROWSORT_CAP];
+    // The triples are only READ (the column passes of the transpose run concurrently on them).
+    __shared__ int32_t sc[ROWSORT_CAP];
     __shared__ double sv[ROWSORT_CAP];
     const int64_t r0 = (int64_t)blockIdx.x * ROWSORT_ROWS;
     const int64_t r = r0 + threadIdx.x;
     const int64_t r1 = min(r0 + (int64_t)ROWSORT_ROWS, n_rows);
     const int A = rowptr[r0], B = rowptr[r1];
     const bool staged = B - A <= ROWSORT_CAP;                                // block-uniform
-    uint64_t *k_ = staged ? sk - A : keys;                                   // indexed by the global entry number
-    double *v_ = staged ? sv - A : vals;
-    if (staged) {
-        for (int i = A + threadIdx.x; i < B; i += ROWSORT_ROWS) { sk[i - A] = keys[i]; sv[i - A] = vals[i]; }
-        __syncthreads();
-    }
+    // the block's entries, unsorted, into shared memory (or, when they do not fit, into the CSR arrays)
+    int32_t *c_ = staged ? sc - A : colidx;                                  // indexed by the global entry number
+    double *v_ = staged ? sv - A : out_vals;
+    for (int i = A + threadIdx.x; i < B; i += ROWSORT_ROWS) { c_[i] = (int32_t)(uint32_t)keys[i]; v_[i] = vals[i]; }
+    __syncthreads();
     if (r < n_rows) {
         const int a = rowptr[r], b = rowptr[r + 1];
         for (int i = a + 1; i < b; ++i) {
-            const uint64_t k = k_[i];
+            const int32_t k = c_[i];
             const double v = v_[i];
             int j = i - 1;
             while (j >= a) {
-                const uint64_t kj = k_[j];
+                const int32_t kj = c_[j];
                 if (kj <= k) break;
-                k_[j + 1] = kj;
+                c_[j + 1] = kj;
                 v_[j + 1] = v_[j];
                 --j;
             }
-            if (j + 1 != i) { k_[j + 1] = k; v_[j + 1] = v; }
+            if (j + 1 != i) { c_[j + 1] = k; v_[j + 1] = v; }
         }
-        if (!staged)
-            for (int j = a; j < b; ++j) { colidx[j] = (int32_t)(uint32_t)keys[j]; out_vals[j] = vals[j]; }
     }
     if (staged) {
         __syncthreads();
-        for (int i = A + threadIdx.x; i < B; i += ROWSORT_ROWS) {
-            const uint64_t k = sk[i - A];
-            const double v = sv[i - A];
-            colidx[i] = (int32_t)(uint32_t)k; out_vals[i] = v;     // (the triples themselves stay row-grouped: all the
-                                                                   //  stable column passes of the transpose need)
-        }
+        for (int i = A + threadIdx.x; i < B; i += ROWSORT_ROWS) { colidx[i] = sc[i - A]; out_vals[i] = sv[i - A]; }
     }
 }
 

@@ -412,3 +412,18 @@ def test_four_times_the_bench_workload(gpu):
     regrid_(xb, transpose(R), y)
     assert abs(float((xb * sa).sum() / (y * da).sum()) - 1) < 1e-12
     print("4x cfg5: build %.2f ms device, %d candidates, %d nnz" % (st["ms_device"], st["n_candidates"], R.intersections.nnz))
+
+
+def test_one_by_one_and_two_by_one(gpu):
+    """nnz = 1 and nnz = 2: the assembly's sorts have nothing (or almost nothing) to do."""
+    one = grids.planar_regular_grid([0.0, 1.0], [0.0, 1.0])
+    two = grids.planar_regular_grid([0.0, 0.5, 1.0], [0.0, 1.0])
+    R = Regridder(one, one)
+    assert R.intersections.nnz == 1 and np.allclose(R.intersections.tocsc().toarray(), [[1.0]])
+    x = np.array([3.0]); y = np.zeros(1)
+    regrid_(y, R, x); assert y[0] == 3.0
+    regrid_(x, transpose(R), y); assert x[0] == 3.0
+    R2 = Regridder(one, two)                                   # 1 x 2
+    assert np.allclose(R2.intersections.tocsc().toarray(), [[0.5, 0.5]])
+    y = np.zeros(1); regrid_(y, R2, np.array([1.0, 3.0])); assert abs(y[0] - 2.0) < 1e-15
+    xb = np.zeros(2); regrid_(xb, transpose(R2), np.array([2.0])); assert np.allclose(xb, [2.0, 2.0])
