@@ -46,27 +46,28 @@ __global__ void __launch_bounds__(NT) clip_kernel(CellsView gd, CellsView gs, co
 // block barriers:
 //   1. 32 pairs at a time, every lane runs the static pre-pass of one pair: empty (area 0, written at
 //      once), untouched (the source cell's own area, when K0's unit-sphere areas are at hand) or the
-//      set of cutting edges; the surviving pairs are appended to one of the warp's three queues in
-//      shared memory, by number of cutting edges (<= 1, 2, >= 3);
+//      set of cutting edges; the surviving pairs are appended to one of the warp's two queues in
+//      shared memory, by number of cutting edges (<= 1, >= 2) -- 16-bit entries, so that the queues
+//      cost no more shared memory than one (a third queue cost a CTA per SM);
 //   2. whenever a queue holds 32 jobs, every lane takes one and runs the cuts + the area -- full warps
 //      (a third of the candidates are false, a quarter of the rest is not cut at all) whose lanes loop
 //      over the same number of cuts.  What is left at the end of the chunk is run in mixed batches.
 // Every pair's area is written exactly once; the non-zero count goes to the tile counter at the end.
 constexpr int CLIP_CHUNK = 512;     // divides CLIP_TILE
-constexpr int CLIP_QUEUES = 3;
+constexpr int CLIP_QUEUES = 2;
 template <int DIM, int NT>
 __global__ void __launch_bounds__(NT) clip_quad_kernel(CellsView gd, CellsView gs, const int2 *__restrict__ pairs,
                                                        int64_t npairs, double thresh,
                                                        const double *__restrict__ unit_src_areas,
                                                        double *__restrict__ area_out, uint32_t *__restrict__ tile_count) {
     extern __shared__ double clip_smem[];
-    __shared__ uint32_t s_queue[NT / 32][CLIP_QUEUES][64];
+    __shared__ uint16_t s_queue[NT / 32][CLIP_QUEUES][64];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t base = ((int64_t)blockIdx.x * (NT / 32) + wid) * CLIP_CHUNK;
     if (base >= npairs) return;
-    uint32_t (*queue)[64] = s_queue[wid];
+    uint16_t (*queue)[64] = s_queue[wid];
     const unsigned lt_mask = (1u << lane) - 1u;
-    int q0 = 0, q1 = 0, q2 = 0, nz = 0;                   // queue lengths (warp-uniform)
+    int q0 = 0, q1 = 0, nz = 0;                           // queue lengths (warp-uniform)
 #pragma unroll 1
     for (int round = 0; round <= CLIP_CHUNK / 32; ++round) {        // the extra round only drains the queues
         const bool last = round == CLIP_CHUNK / 32;
@@ -84,14 +85,12 @@ __global__ void __launch_bounds__(NT) clip_quad_kernel(CellsView gd, CellsView g
             }
         }
         const int ncut = __popc((unsigned)max(state, 0));
-        const int cls = state < 0 ? -1 : (ncut <= 1 ? 0 : (ncut == 2 ? 1 : 2));
-        const uint32_t job = (uint32_t)(round * 32 + lane) | ((uint32_t)max(state, 0) << 10);
-        const unsigned b0 = __ballot_sync(CRG_FULL, cls == 0), b1 = __ballot_sync(CRG_FULL, cls == 1),
-                       b2 = __ballot_sync(CRG_FULL, cls == 2);
+        const int cls = state < 0 ? -1 : (ncut <= 1 ? 0 : 1);
+        const uint16_t job = (uint16_t)((round * 32 + lane) | (max(state, 0) << 9));      // 9 bits pair, 4 bits edges
+        const unsigned b0 = __ballot_sync(CRG_FULL, cls == 0), b1 = __ballot_sync(CRG_FULL, cls == 1);
         if (cls == 0) queue[0][q0 + __popc(b0 & lt_mask)] = job;
         if (cls == 1) queue[1][q1 + __popc(b1 & lt_mask)] = job;
-        if (cls == 2) queue[2][q2 + __popc(b2 & lt_mask)] = job;
-        q0 += __popc(b0); q1 += __popc(b1); q2 += __popc(b2);
+        q0 += __popc(b0); q1 += __popc(b1);
         __syncwarp();
 #pragma unroll 1
         for (;;) {
@@ -99,20 +98,18 @@ __global__ void __launch_bounds__(NT) clip_quad_kernel(CellsView gd, CellsView g
             bool have = false;
             if (q0 >= 32) { q0 -= 32; j = queue[0][q0 + lane]; have = true; }
             else if (q1 >= 32) { q1 -= 32; j = queue[1][q1 + lane]; have = true; }
-            else if (q2 >= 32) { q2 -= 32; j = queue[2][q2 + lane]; have = true; }
-            else if (last && q0 + q1 + q2 > 0) {           // leftovers: one mixed batch, queue 0 first
-                const int t0 = min(q0, 32), t1 = min(q1, 32 - t0), t2 = min(q2, 32 - t0 - t1);
+            else if (last && q0 + q1 > 0) {                // leftovers: one mixed batch, queue 0 first
+                const int t0 = min(q0, 32), t1 = min(q1, 32 - t0);
                 if (lane < t0) { j = queue[0][q0 - t0 + lane]; have = true; }
                 else if (lane < t0 + t1) { j = queue[1][q1 - t1 + (lane - t0)]; have = true; }
-                else if (lane < t0 + t1 + t2) { j = queue[2][q2 - t2 + (lane - t0 - t1)]; have = true; }
-                q0 -= t0; q1 -= t1; q2 -= t2;
+                q0 -= t0; q1 -= t1;
             } else {
                 break;
             }
             if (have) {
-                const int64_t jdx = base + (j & 1023u);
+                const int64_t jdx = base + (j & 511u);
                 const int2 pr = pairs[jdx];
-                double area = quad_cut_area<DIM, NT>(gs, pr.x, gd, pr.y, j >> 10, clip_smem);
+                double area = quad_cut_area<DIM, NT>(gs, pr.x, gd, pr.y, j >> 9, clip_smem);
                 if (!(area > thresh) || !(area > 0.0)) area = 0.0;     // `area > 0` (intersection_areas.jl:24); NaN drops too
                 area_out[jdx] = area;
                 nz += area != 0.0;
