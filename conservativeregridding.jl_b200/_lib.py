@@ -32,6 +32,7 @@ EXPORTS = [
     "crg_export_csc", "crg_export_csr", "crg_candidates", "crg_normalize", "crg_maximum", "crg_scale", "crg_apply", "crg_apply_async",
     "crg_set_stream", "crg_synchronize", "crg_apply_bytes", "crg_last_error", "crg_device_count", "crg_version",
     "crg_fp64_peak", "crg_launch_count", "crg_build_grids", "crg_grid_ncells", "crg_grid_cells",
+    "crg_clip_pairs", "crg_set_areas",
 ]
 
 
@@ -127,6 +128,8 @@ def lib():
     L.crg_dims.argtypes = [vp, P(i64), P(i64), P(i64)]
     L.crg_stats.argtypes = [vp, P(BuildStats)]
     L.crg_areas.argtypes = [vp, vp, vp]
+    L.crg_set_areas.argtypes = [vp, vp, vp]
+    L.crg_clip_pairs.argtypes = [P(Options), P(Cells), P(Cells), i64, vp, vp, vp]
     L.crg_export_csc.argtypes = [vp, i32, vp, vp, vp]
     L.crg_export_csr.argtypes = [vp, i32, vp, vp, vp]
     L.crg_candidates.argtypes = [vp, vp, vp]

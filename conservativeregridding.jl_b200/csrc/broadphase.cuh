@@ -190,6 +190,36 @@ __device__ __forceinline__ const double *stage_cell(const CellsView &g, int64_t 
 // --- bounds: per-cell diameter + grid statistics -----------------------------------------
 // K4 + K1 in one pass over the vertices: geometric area (x scale) and orientation flag of every cell
 // (regridder.jl:165-178), its diameter, and the grid statistics the bin grid is chosen from.
+// Convexity of a ring (both clip operators here are convex-convex Sutherland-Hodgman, like the reference's
+// ConvexConvexSutherlandHodgman on the sphere, regridder.jl:96-103; the reference's planar operator is
+// Foster-Hormann, :87-94, which also takes non-convex rings -- those are DETECTED here so that the build
+// fails with CRG_ERR_UNSUPPORTED instead of returning a wrong area).  Every vertex must lie on the inner
+// side of every edge, up to round-off: h_e(w) * orientation >= -tol * |n_e| * diameter.
+template <int DIM>
+__device__ __forceinline__ bool ring_is_convex(const double *p, int n, bool clockwise, double diam) {
+    const double sg = clockwise ? -1.0 : 1.0;
+    for (int e = 0; e < n; ++e) {
+        const double *u = p + DIM * e, *v = p + DIM * (e + 1 == n ? 0 : e + 1);
+        double nx, ny, nz = 0.0, h0 = 0.0;
+        if (DIM == 3) {
+            nx = u[1] * v[2] - u[2] * v[1]; ny = u[2] * v[0] - u[0] * v[2]; nz = u[0] * v[1] - u[1] * v[0];
+        } else {
+            nx = -(v[1] - u[1]); ny = v[0] - u[0];
+            h0 = -(nx * u[0] + ny * u[1]);
+        }
+        // + the round-off of h itself: ~eps for unit vectors, ~eps |n| max|coordinate| in the plane
+        const double nn = sqrt(nx * nx + ny * ny + nz * nz);
+        const double tol = DIM == 3 ? 1e-9 * nn * diam + 1e-14
+                                    : nn * (1e-9 * diam + 1e-14 * (fabs(u[0]) + fabs(u[1]) + fabs(v[0]) + fabs(v[1])));
+        for (int i = 0; i < n; ++i) {
+            const double *w = p + DIM * i;
+            const double h = DIM == 3 ? nx * w[0] + ny * w[1] + nz * w[2] : nx * w[0] + ny * w[1] + h0;
+            if (sg * h < -tol) return false;
+        }
+    }
+    return true;
+}
+
 template <int DIM>
 __global__ void __launch_bounds__(256) bp_bounds_kernel(CellsView g, float *__restrict__ diam, BPStats *st,
                                                         float big_chord, double scale, double *__restrict__ areas,
@@ -213,6 +243,7 @@ __global__ void __launch_bounds__(256) bp_bounds_kernel(CellsView g, float *__re
         if (f) atomicAdd(nflip, 1u);
         const float d = cell_diameter<DIM>(p, n);
         diam[c] = d;
+        if (!ring_is_convex<DIM>(p, n, f, (double)d)) atomicAdd(nflip + 2, 1u);   // nflip[2..3]: non-convex cells
         if (DIM == 2 || d < big_chord) {
             sum = d; mx = d; cnt = 1;
             for (int i = 0; i < n; ++i)

@@ -124,6 +124,27 @@ __global__ void __launch_bounds__(256) check_offsets_kernel(const int32_t *off, 
     }
 }
 
+__global__ void __launch_bounds__(256) check_coo_kernel(const int64_t *rows, const int64_t *cols, int64_t n,
+                                                        int64_t n_rows, int64_t n_cols, int *bad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && (rows[i] < 0 || rows[i] >= n_rows || cols[i] < 0 || cols[i] >= n_cols)) atomicExch(bad, 1);
+}
+
+// (src, dst) index lists -> int2 pairs, range-checked
+__global__ void __launch_bounds__(256) pack_pairs_kernel(const int64_t *src_idx, const int64_t *dst_idx, int64_t n,
+                                                         int64_t n_src, int64_t n_dst, int2 *pairs, int *bad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t a = src_idx[i], b = dst_idx[i];
+    const bool ok = a >= 0 && a < n_src && b >= 0 && b < n_dst;
+    if (!ok) atomicExch(bad, 1);
+    pairs[i] = ok ? make_int2((int)a, (int)b) : make_int2(0, 0);
+}
+__global__ void __launch_bounds__(256) scale_kernel(double *v, int64_t n, double f) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] *= f;
+}
+
 static int stage_cells(const crg_cells *c, int dim, cudaStream_t st, DevCells *out, const char *name) {
     const int64_t n = c->ncells;
     out->view.ncells = n;
@@ -523,6 +544,38 @@ static int do_normalize(crg_regridder *R) {
 
 static int device_side_stream(int dev, cudaStream_t *out);
 
+// K3 launcher: dense areas of `n_cand` (src, dst) pairs + survivor counts per CLIP_TILE pairs (kernels.cuh).
+// Quadrilateral grids take the symbolic-polygon kernel, everything else the general one.
+template <int DIM>
+static int launch_clip(const CellsView &gdv, const CellsView &gsv, bool fixed, int nv_dst, int nv_src, const int2 *pairs,
+                       int64_t n_cand, double thresh, const double *unit_src_areas, double *pair_area,
+                       uint32_t *tile_count, cudaStream_t st) {
+    static const bool allow_quad = !(getenv("CRG_CLIP_QUAD") && atoi(getenv("CRG_CLIP_QUAD")) == 0);
+    const bool fixed4 = fixed && nv_dst <= 4 && nv_src <= 4;
+    const bool quad = allow_quad && fixed4 && nv_dst == 4 && nv_src == 4 && ((uintptr_t)gdv.verts % 16 == 0) &&
+                      ((uintptr_t)gsv.verts % 16 == 0);
+#define CRG_CLIP(NT_, MW_)                                                                                            \
+    do {                                                                                                              \
+        const size_t smem = sizeof(double) * 2 * MW_ * DIM * NT_;                                                     \
+        auto kern = clip_kernel<DIM, NT_, MW_>;                                                                       \
+        CRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+        kern<<<ceil_div(n_cand, NT_), NT_, smem, st>>>(gdv, gsv, pairs, n_cand, thresh, pair_area, tile_count);       \
+    } while (0)
+    if (quad) {
+        constexpr int NT = 128;
+        const size_t smem = sizeof(double) * QUAD_SLOTS * DIM * NT;
+        auto kern = clip_quad_kernel<DIM, NT>;
+        CRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // an untouched source cell contributes its own area: reuse K4's (only when they are unit-sphere areas)
+        kern<<<ceil_div(ceil_div(n_cand, CLIP_CHUNK), NT / 32), NT, smem, st>>>(gdv, gsv, pairs, n_cand, thresh,
+                                                                                unit_src_areas, pair_area, tile_count);
+    } else if (fixed4) CRG_CLIP(128, 8);
+    else CRG_CLIP(64, 2 * CRG_MAX_VERTS);
+#undef CRG_CLIP
+    CRG_LAUNCH_CHECK();
+    return CRG_OK;
+}
+
 template <int DIM>
 static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *src) {
     cudaStream_t st = R->stream;
@@ -545,9 +598,9 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     CRG_TRY(R->src_areas.alloc((size_t)ns, st));
     CRG_TRY(gd.flip.alloc_tmp((size_t)nd, st));
     CRG_TRY(gs.flip.alloc_tmp((size_t)ns, st));
-    DevBuf<unsigned int> nflip;
-    CRG_TRY(nflip.alloc_tmp(2, st));
-    CRG_CUDA(cudaMemsetAsync(nflip.p, 0, 2 * sizeof(unsigned int), st));
+    DevBuf<unsigned int> nflip;      // [0..1] clockwise cells (dst, src), [2..3] non-convex cells (dst, src)
+    CRG_TRY(nflip.alloc_tmp(4, st));
+    CRG_CUDA(cudaMemsetAsync(nflip.p, 0, 4 * sizeof(unsigned int), st));
     CRG_TRY(tm.mark());   // 1
 
     // ---- K1: bounds -------------------------------------------------------------------------
@@ -566,8 +619,15 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     if (ns) { bp_bounds_kernel<DIM><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, gs.diam.p, dstats.p + 1, (float)big_chord, r2, R->src_areas.p, gs.flip.p, nflip.p + 1); CRG_LAUNCH_CHECK(); }
     gd.view.flip = gd.flip.p;
     gs.view.flip = gs.flip.p;
+    unsigned int h_nflip[4] = {0, 0, 0, 0};
     CRG_CUDA(cudaMemcpyAsync(hst, dstats.p, sizeof(hst), cudaMemcpyDeviceToHost, st));
+    CRG_CUDA(cudaMemcpyAsync(h_nflip, nflip.p, sizeof(h_nflip), cudaMemcpyDeviceToHost, st));
     CRG_CUDA(cudaStreamSynchronize(st));
+    if (h_nflip[2] || h_nflip[3])
+        return set_error(CRG_ERR_UNSUPPORTED,
+                         "%u destination and %u source cells are not convex: the device clip is convex-convex "
+                         "Sutherland-Hodgman (split such cells into convex parts; the Python front end does it for planar grids)",
+                         h_nflip[2], h_nflip[3]);
     CRG_TRY(tm.mark());   // 2
 
     // ---- choose the bin grid ----------------------------------------------------------------
@@ -727,31 +787,9 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
         CRG_TRY(pair_area.alloc_tmp((size_t)n_cand, st));
         CRG_TRY(tile_count.alloc_tmp((size_t)ntiles + 1, st));
         CRG_CUDA(cudaMemsetAsync(tile_count.p, 0, sizeof(uint32_t) * ((size_t)ntiles + 1), st));
-        static const bool allow_quad = !(getenv("CRG_CLIP_QUAD") && atoi(getenv("CRG_CLIP_QUAD")) == 0);
-        const bool fixed4 = !dst->offsets && !src->offsets && dst->nv <= 4 && src->nv <= 4;
-        const bool quad = allow_quad && fixed4 && dst->nv == 4 && src->nv == 4 &&
-                          ((uintptr_t)gd.view.verts % 16 == 0) && ((uintptr_t)gs.view.verts % 16 == 0);
-#define CRG_CLIP(NT_, MW_)                                                                                            \
-    do {                                                                                                              \
-        const size_t smem = sizeof(double) * 2 * MW_ * DIM * NT_;                                                     \
-        auto kern = clip_kernel<DIM, NT_, MW_>;                                                                       \
-        CRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
-        kern<<<ceil_div(n_cand, NT_), NT_, smem, st>>>(gd.view, gs.view, pairs.p, n_cand, R->opts.area_threshold,     \
-                                                       pair_area.p, tile_count.p);                                    \
-    } while (0)
-        if (quad) {
-            constexpr int NT = 128;
-            const size_t smem = sizeof(double) * QUAD_SLOTS * DIM * NT;
-            auto kern = clip_quad_kernel<DIM, NT>;
-            CRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            // an untouched source cell contributes its own area: reuse K0's (only when they are unit-sphere areas)
-            const double *unit_src_areas = r2 == 1.0 ? R->src_areas.p : nullptr;
-            kern<<<ceil_div(ceil_div(n_cand, CLIP_CHUNK), NT / 32), NT, smem, st>>>(
-                gd.view, gs.view, pairs.p, n_cand, R->opts.area_threshold, unit_src_areas, pair_area.p, tile_count.p);
-        } else if (fixed4) CRG_CLIP(128, 8);
-        else CRG_CLIP(64, 2 * CRG_MAX_VERTS);
-#undef CRG_CLIP
-        CRG_LAUNCH_CHECK();
+        CRG_TRY((launch_clip<DIM>(gd.view, gs.view, !dst->offsets && !src->offsets, dst->nv, src->nv, pairs.p, n_cand,
+                                  R->opts.area_threshold, r2 == 1.0 ? R->src_areas.p : nullptr, pair_area.p,
+                                  tile_count.p, st)));
         CRG_TRY((exclusive_scan<uint32_t, uint32_t>(tile_count.p, ntiles, tile_count.p, st)));
         CRG_CUDA(cudaMemcpyAsync(&h_keep, tile_count.p + ntiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CRG_CUDA(cudaStreamSynchronize(st));
@@ -797,6 +835,66 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     S.ms_finish = tm.ms(t2, last);
     S.ms_device = tm.ms(0, last);
     S.ms_total = now_ms() - t_begin;
+    return CRG_OK;
+}
+
+// compute_intersection_areas (intersection_areas.jl:4-32) for an explicit pair list, with the kernels of the build.
+template <int DIM>
+static int clip_pairs_impl(const crg_options *opts, const crg_cells *dst, const crg_cells *src, int64_t n_pairs,
+                           const int64_t *src_idx, const int64_t *dst_idx, double *area_out, cudaStream_t st) {
+    DevCells gd, gs;
+    CRG_TRY(stage_cells(dst, DIM, st, &gd, "dst"));
+    CRG_TRY(stage_cells(src, DIM, st, &gs, "src"));
+    const int64_t nd = dst->ncells, ns = src->ncells;
+    DevBuf<double> a_dst, a_src;
+    DevBuf<unsigned int> nflip;
+    DevBuf<BPStats> dstats;
+    CRG_TRY(a_dst.alloc_tmp((size_t)nd, st));
+    CRG_TRY(a_src.alloc_tmp((size_t)ns, st));
+    CRG_TRY(gd.flip.alloc_tmp((size_t)nd, st));
+    CRG_TRY(gs.flip.alloc_tmp((size_t)ns, st));
+    CRG_TRY(gd.diam.alloc_tmp((size_t)nd, st));
+    CRG_TRY(gs.diam.alloc_tmp((size_t)ns, st));
+    CRG_TRY(nflip.alloc_tmp(4, st));
+    CRG_TRY(dstats.alloc_tmp(2, st));
+    CRG_CUDA(cudaMemsetAsync(nflip.p, 0, 4 * sizeof(unsigned int), st));
+    CRG_CUDA(cudaMemsetAsync(dstats.p, 0, 2 * sizeof(BPStats), st));
+    if (nd) { bp_bounds_kernel<DIM><<<ceil_div(nd, 256), 256, 0, st>>>(gd.view, gd.diam.p, dstats.p, 1e30f, 1.0, a_dst.p, gd.flip.p, nflip.p); CRG_LAUNCH_CHECK(); }
+    if (ns) { bp_bounds_kernel<DIM><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, gs.diam.p, dstats.p + 1, 1e30f, 1.0, a_src.p, gs.flip.p, nflip.p + 1); CRG_LAUNCH_CHECK(); }
+    gd.view.flip = gd.flip.p;
+    gs.view.flip = gs.flip.p;
+    DevBuf<int64_t> di, si;
+    DevBuf<int2> pairs;
+    DevBuf<int> bad;
+    DevBuf<double> pair_area;
+    DevBuf<uint32_t> tile_count;
+    const int64_t ntiles = (n_pairs + CLIP_TILE - 1) / CLIP_TILE;
+    CRG_TRY(di.alloc_tmp((size_t)n_pairs, st));
+    CRG_TRY(si.alloc_tmp((size_t)n_pairs, st));
+    CRG_TRY(pairs.alloc_tmp((size_t)n_pairs, st));
+    CRG_TRY(bad.alloc_tmp(1, st));
+    CRG_TRY(pair_area.alloc_tmp((size_t)n_pairs, st));
+    CRG_TRY(tile_count.alloc_tmp((size_t)ntiles + 1, st));
+    CRG_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
+    CRG_CUDA(cudaMemsetAsync(tile_count.p, 0, sizeof(uint32_t) * ((size_t)ntiles + 1), st));
+    CRG_CUDA(cudaMemcpyAsync(si.p, src_idx, sizeof(int64_t) * (size_t)n_pairs, cudaMemcpyDefault, st));
+    CRG_CUDA(cudaMemcpyAsync(di.p, dst_idx, sizeof(int64_t) * (size_t)n_pairs, cudaMemcpyDefault, st));
+    pack_pairs_kernel<<<ceil_div(n_pairs, 256), 256, 0, st>>>(si.p, di.p, n_pairs, ns, nd, pairs.p, bad.p);
+    CRG_LAUNCH_CHECK();
+    unsigned int h_nflip[4] = {0, 0, 0, 0};
+    int hb = 0;
+    CRG_CUDA(cudaMemcpyAsync(h_nflip, nflip.p, sizeof(h_nflip), cudaMemcpyDeviceToHost, st));
+    CRG_CUDA(cudaMemcpyAsync(&hb, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CRG_CUDA(cudaStreamSynchronize(st));
+    if (hb) return set_error(CRG_ERR_INVALID, "crg_clip_pairs: a cell index is out of range");
+    if (h_nflip[2] || h_nflip[3])
+        return set_error(CRG_ERR_UNSUPPORTED, "%u destination and %u source cells are not convex", h_nflip[2], h_nflip[3]);
+    CRG_TRY((launch_clip<DIM>(gd.view, gs.view, !dst->offsets && !src->offsets, dst->nv, src->nv, pairs.p, n_pairs,
+                              opts->area_threshold, a_src.p, pair_area.p, tile_count.p, st)));
+    const double r2 = DIM == 3 ? opts->radius * opts->radius : 1.0;
+    if (r2 != 1.0) { scale_kernel<<<ceil_div(n_pairs, 256), 256, 0, st>>>(pair_area.p, n_pairs, r2); CRG_LAUNCH_CHECK(); }
+    CRG_CUDA(cudaMemcpyAsync(area_out, pair_area.p, sizeof(double) * (size_t)n_pairs, cudaMemcpyDefault, st));
+    CRG_CUDA(cudaStreamSynchronize(st));
     return CRG_OK;
 }
 
@@ -885,13 +983,34 @@ static int new_handle(const crg_options *opts, crg_regridder **out, DeviceGuard 
     return CRG_OK;
 }
 
+// A failed build may have forked work to the device's side stream (assemble): both streams are drained before
+// the temporaries (arena) and the handle's buffers are released.
+static void drain_after_failure(crg_regridder *R) {
+    cudaStreamSynchronize(R->stream);
+    if (R->device >= 0 && R->device < 64 && g_dev_stream2[R->device]) cudaStreamSynchronize(g_dev_stream2[R->device]);
+    cudaGetLastError();
+}
+
 static void destroy_handle(crg_regridder *R) {
     if (!R) return;
     int prev = -1;
     cudaGetDevice(&prev);
     cudaSetDevice(R->device);
     cudaStream_t st = R->own_stream;
-    // release everything on the handle's own stream, then drain it
+    // Everything is released (stream-ordered) on the library stream.  Work may still be in flight on a caller
+    // stream (crg_options.stream / crg_set_stream + crg_apply_async): the library stream first waits for it,
+    // so the pool cannot hand the matrix to another allocation while a kernel still reads it.
+    if (R->stream && R->stream != st) {
+        cudaEvent_t ev = nullptr;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) {
+            if (cudaEventRecord(ev, R->stream) != cudaSuccess || cudaStreamWaitEvent(st, ev, 0) != cudaSuccess)
+                cudaStreamSynchronize(R->stream);
+            cudaEventDestroy(ev);
+        } else {
+            cudaStreamSynchronize(R->stream);
+        }
+        cudaGetLastError();
+    }
     auto rebind = [&](auto &buf) { buf.s = st; buf.release(); };
     rebind(R->A.rowptr); rebind(R->A.colidx); rebind(R->A.vals);
     rebind(R->At.rowptr); rebind(R->At.colidx); rebind(R->At.vals);
@@ -1129,7 +1248,7 @@ int crg_build(const crg_options *opts, const crg_cells *dst, const crg_cells *sr
         ArenaScope arena;
         rc = arena.begin(R->device, R->stream);
         if (rc == CRG_OK) rc = opts->manifold == CRG_SPHERICAL ? build_impl<3>(R, dst, src) : build_impl<2>(R, dst, src);
-        if (rc != CRG_OK) cudaStreamSynchronize(R->stream);
+        if (rc != CRG_OK) drain_after_failure(R);
     }
     if (rc != CRG_OK) { destroy_handle(R); return rc; }
     *out = R;
@@ -1198,7 +1317,7 @@ int crg_build_grids(const crg_options *opts, const crg_grid *dst, const crg_grid
         if (rc == CRG_OK) rc = materialise(dst, nd, vd, &cd);
         if (rc == CRG_OK) rc = materialise(src, ns, vs, &cs);
         if (rc == CRG_OK) rc = build_impl<3>(R, &cd, &cs);
-        if (rc != CRG_OK) cudaStreamSynchronize(R->stream);
+        if (rc != CRG_OK) drain_after_failure(R);
     }
     if (rc != CRG_OK) { destroy_handle(R); return rc; }
     *out = R;
@@ -1213,10 +1332,11 @@ int crg_build_from_coo(const crg_options *opts, int64_t n_dst, int64_t n_src, in
     if (n_dst < 0 || n_src < 0 || nnz < 0 || n_dst >= ((int64_t)1 << 31) || n_src >= ((int64_t)1 << 31))
         return set_error(CRG_ERR_INVALID, "crg_build_from_coo: bad sizes");
     if (nnz > 0 && (!dst_idx || !src_idx || !area)) return set_error(CRG_ERR_INVALID, "crg_build_from_coo: null triples");
-    if (!is_device_ptr(dst_idx))
-        for (int64_t k = 0; k < nnz; ++k)
-            if (dst_idx[k] < 0 || dst_idx[k] >= n_dst || src_idx[k] < 0 || src_idx[k] >= n_src)
-                return set_error(CRG_ERR_INVALID, "crg_build_from_coo: index out of range at entry %lld", (long long)k);
+    // host-resident index arrays are range-checked here, device-resident ones by check_coo_kernel below
+    const bool dst_idx_dev = is_device_ptr(dst_idx), src_idx_dev = is_device_ptr(src_idx);
+    for (int64_t k = 0; k < nnz; ++k)
+        if ((!dst_idx_dev && (dst_idx[k] < 0 || dst_idx[k] >= n_dst)) || (!src_idx_dev && (src_idx[k] < 0 || src_idx[k] >= n_src)))
+            return set_error(CRG_ERR_INVALID, "crg_build_from_coo: index out of range at entry %lld", (long long)k);
     DeviceGuard guard;
     crg_regridder *R = nullptr;
     CRG_TRY(new_handle(opts, &R, guard));
@@ -1235,6 +1355,17 @@ int crg_build_from_coo(const crg_options *opts, int64_t n_dst, int64_t n_src, in
             CRG_CUDA(cudaMemcpyAsync(dr.p, dst_idx, sizeof(int64_t) * nnz, cudaMemcpyDefault, st));
             CRG_CUDA(cudaMemcpyAsync(dc.p, src_idx, sizeof(int64_t) * nnz, cudaMemcpyDefault, st));
             CRG_CUDA(cudaMemcpyAsync(vals.p, area, sizeof(double) * nnz, cudaMemcpyDefault, st));
+            if (dst_idx_dev || src_idx_dev) {
+                DevBuf<int> bad;
+                CRG_TRY(bad.alloc_tmp(1, st));
+                CRG_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
+                check_coo_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(dr.p, dc.p, nnz, n_dst, n_src, bad.p);
+                CRG_LAUNCH_CHECK();
+                int hb = 0;
+                CRG_CUDA(cudaMemcpyAsync(&hb, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+                CRG_CUDA(cudaStreamSynchronize(st));
+                if (hb) return set_error(CRG_ERR_INVALID, "crg_build_from_coo: an index is out of range");
+            }
             pack_coo_kernel<<<ceil_div(nnz, 256), 256, 0, st>>>(dr.p, dc.p, nnz, keys.p);
             CRG_LAUNCH_CHECK();
         }
@@ -1262,10 +1393,47 @@ int crg_build_from_coo(const crg_options *opts, int64_t n_dst, int64_t n_src, in
         ArenaScope arena;
         rc = arena.begin(R->device, R->stream);
         if (rc == CRG_OK) rc = body();
-        if (rc != CRG_OK) cudaStreamSynchronize(R->stream);
+        if (rc != CRG_OK) drain_after_failure(R);
     }
     if (rc != CRG_OK) { destroy_handle(R); return rc; }
     *out = R;
+    return CRG_OK;
+}
+
+int crg_clip_pairs(const crg_options *opts, const crg_cells *dst, const crg_cells *src, int64_t n_pairs,
+                   const int64_t *src_idx, const int64_t *dst_idx, double *area_out) {
+    if (!opts) return set_error(CRG_ERR_INVALID, "crg_clip_pairs: null options");
+    if (n_pairs < 0 || n_pairs >= ((int64_t)1 << 32)) return set_error(CRG_ERR_INVALID, "crg_clip_pairs: bad pair count");
+    if (n_pairs > 0 && (!src_idx || !dst_idx || !area_out)) return set_error(CRG_ERR_INVALID, "crg_clip_pairs: null argument");
+    if (opts->manifold != CRG_PLANAR && opts->manifold != CRG_SPHERICAL)
+        return set_error(CRG_ERR_INVALID, "crg_clip_pairs: unknown manifold %d", opts->manifold);
+    if (!(opts->radius > 0.0)) return set_error(CRG_ERR_INVALID, "crg_clip_pairs: radius must be positive");
+    CRG_TRY(validate_cells(dst, "dst"));
+    CRG_TRY(validate_cells(src, "src"));
+    CRG_TRY(check_device_available());
+    if (n_pairs == 0) return CRG_OK;
+    DeviceGuard guard;
+    CRG_TRY(guard.set(opts->device));
+    int dev = 0;
+    CRG_CUDA(cudaGetDevice(&dev));
+    cudaStream_t st = (cudaStream_t)opts->stream;
+    if (!st) CRG_TRY(device_stream(dev, &st));
+    ArenaScope arena;
+    int rc = arena.begin(dev, st);
+    if (rc == CRG_OK)
+        rc = opts->manifold == CRG_SPHERICAL ? clip_pairs_impl<3>(opts, dst, src, n_pairs, src_idx, dst_idx, area_out, st)
+                                             : clip_pairs_impl<2>(opts, dst, src, n_pairs, src_idx, dst_idx, area_out, st);
+    if (rc != CRG_OK) { cudaStreamSynchronize(st); cudaGetLastError(); }
+    return rc;
+}
+
+int crg_set_areas(crg_regridder *r, const double *dst_areas, const double *src_areas) {
+    if (!r) return set_error(CRG_ERR_INVALID, "null regridder");
+    DeviceGuard guard;
+    CRG_TRY(guard.set(r->device));
+    if (dst_areas && r->n_dst) CRG_CUDA(cudaMemcpyAsync(r->dst_areas.p, dst_areas, sizeof(double) * (size_t)r->n_dst, cudaMemcpyDefault, r->stream));
+    if (src_areas && r->n_src) CRG_CUDA(cudaMemcpyAsync(r->src_areas.p, src_areas, sizeof(double) * (size_t)r->n_src, cudaMemcpyDefault, r->stream));
+    CRG_CUDA(cudaStreamSynchronize(r->stream));
     return CRG_OK;
 }
 
@@ -1371,8 +1539,16 @@ int crg_set_stream(crg_regridder *r, void *s) {
     if (!r) return set_error(CRG_ERR_INVALID, "null regridder");
     DeviceGuard guard;
     CRG_TRY(guard.set(r->device));
-    CRG_CUDA(cudaStreamSynchronize(r->stream));
-    r->stream = s ? (cudaStream_t)s : r->own_stream;
+    cudaStream_t ns = s ? (cudaStream_t)s : r->own_stream;
+    if (ns == r->stream) return CRG_OK;
+    // work already enqueued on the old stream stays ahead of what follows on the new one (no host wait)
+    cudaEvent_t ev;
+    CRG_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(ev, r->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ns, ev, 0);
+    cudaEventDestroy(ev);
+    CRG_CUDA(e);
+    r->stream = ns;
     return CRG_OK;
 }
 

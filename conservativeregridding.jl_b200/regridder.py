@@ -109,6 +109,9 @@ def _cells_struct(g: Grid, keep: list) -> _lib.Cells:
     c = _lib.Cells()
     v = g.verts
     if _is_torch(v):
+        import torch
+        if v.dtype != torch.float64 or not v.is_contiguous():
+            v = v.to(torch.float64).contiguous()
         keep.append(v)
         c.verts = v.data_ptr()
     else:
@@ -118,6 +121,9 @@ def _cells_struct(g: Grid, keep: list) -> _lib.Cells:
     if g.offsets is not None:
         o = g.offsets
         if _is_torch(o):
+            import torch
+            if o.dtype != torch.int32 or not o.is_contiguous():
+                o = o.to(torch.int32).contiguous()
             keep.append(o)
             c.offsets = o.data_ptr()
         else:
@@ -136,11 +142,23 @@ def _cells_struct(g: Grid, keep: list) -> _lib.Cells:
 # the matrix handle
 # -----------------------------------------------------------------------------------------
 
+CUDA_STREAM_LEGACY = 1      # cudaStreamLegacy: the legacy default stream, named explicitly (0 / None = library stream)
+
+
+def torch_stream_ptr(device=None) -> int:
+    """``cudaStream_t`` of torch's current stream on ``device`` as the library wants it: torch reports the
+    legacy default stream as 0, which the C ABI reserves for "the handle's own stream"."""
+    import torch
+    s = torch.cuda.current_stream(device).cuda_stream
+    return s if s else CUDA_STREAM_LEGACY
+
+
 class _Handle:
     """Owns one ``crg_regridder*``; freed with the last reference (Julia finalizer analogue)."""
 
-    def __init__(self, ptr):
+    def __init__(self, ptr, stream=None):
         self.ptr = ptr
+        self.stream = stream or None      # the cudaStream_t the handle currently runs on (None = its own)
 
     def __del__(self):
         try:
@@ -227,8 +245,20 @@ class B200Matrix:
         _lib.check(_lib.lib().crg_candidates(self._h.ptr, s.ctypes.data, d.ctypes.data))
         return s, d
 
-    def set_stream(self, cuda_stream_ptr: int):
-        _lib.check(_lib.lib().crg_set_stream(self._h.ptr, C.c_void_p(cuda_stream_ptr or None)))
+    def set_stream(self, cuda_stream_ptr: Optional[int]):
+        """Run on a caller stream: None = the library's own stream, 0 = the legacy default stream
+        (``cudaStreamLegacy``), anything else a ``cudaStream_t``.  No host synchronisation."""
+        if cuda_stream_ptr is not None and cuda_stream_ptr == 0:
+            cuda_stream_ptr = CUDA_STREAM_LEGACY
+        if cuda_stream_ptr == self._h.stream:
+            return
+        _lib.check(_lib.lib().crg_set_stream(self._h.ptr, C.c_void_p(cuda_stream_ptr)))
+        self._h.stream = cuda_stream_ptr
+
+    def follow_torch_stream(self, tensor):
+        """CUDA-tensor applies run on torch's current stream of the tensor's device, so that they are
+        ordered after the kernels that produced the inputs and before whatever consumes the outputs."""
+        self.set_stream(torch_stream_ptr(tensor.device))
 
     def synchronize(self):
         _lib.check(_lib.lib().crg_synchronize(self._h.ptr))
@@ -303,7 +333,33 @@ def _refresh_areas(R: RegridderB200):
     M = R.intersections
     da = R.src_areas if M.transposed else R.dst_areas
     sa = R.dst_areas if M.transposed else R.src_areas
-    _lib.check(_lib.lib().crg_areas(M._h.ptr, da.ctypes.data, sa.ctypes.data))
+    for a in (da, sa):
+        a.flags.writeable = True
+    try:
+        _lib.check(_lib.lib().crg_areas(M._h.ptr, da.ctypes.data, sa.ctypes.data))
+    finally:
+        for a in (da, sa):
+            a.flags.writeable = False
+
+
+def set_areas(R: RegridderB200, dst_areas=None, src_areas=None) -> RegridderB200:
+    """Replace ``R.dst_areas`` / ``R.src_areas`` (the reference lets a user edit them in place, and
+    ``regrid!`` divides by them, regrid.jl:104-118): pushed to the device copy the fused division uses
+    (``crg_set_areas``) and mirrored in the shared host vectors.  For transpose(R) the roles are swapped."""
+    M = R.intersections
+    n_out, n_in = M.shape
+    vals = []
+    for v, n, name in ((dst_areas, n_out, "dst_areas"), (src_areas, n_in, "src_areas")):
+        if v is not None:
+            v = np.ascontiguousarray(v, dtype=np.float64)
+            if v.shape != (n,):
+                raise DimensionMismatch(f"{name} must have {n} entries, got {v.shape}")
+        vals.append(v)
+    d, s_ = (vals[1], vals[0]) if M.transposed else (vals[0], vals[1])
+    _lib.check(_lib.lib().crg_set_areas(M._h.ptr, d.ctypes.data if d is not None else None,
+                                        s_.ctypes.data if s_ is not None else None))
+    _refresh_areas(R)
+    return R
 
 
 def areas_to(R: RegridderB200, dst_areas_out=None, src_areas_out=None):
@@ -356,8 +412,8 @@ def _host_empty(n: int) -> np.ndarray:
     return np.empty(n)
 
 
-def _wrap(ptr, n_dst, n_src) -> RegridderB200:
-    h = _Handle(ptr)
+def _wrap(ptr, n_dst, n_src, stream=None) -> RegridderB200:
+    h = _Handle(ptr, stream)
     M = B200Matrix(h, n_dst, n_src)
 
     def fetch(which):
@@ -365,6 +421,9 @@ def _wrap(ptr, n_dst, n_src) -> RegridderB200:
             a = _host_empty(n_dst if which == 0 else n_src)
             _lib.check(_lib.lib().crg_areas(h.ptr, a.ctypes.data if which == 0 else None,
                                             a.ctypes.data if which == 1 else None))
+            # the fused division of regrid! uses the DEVICE copy: in-place edits of this host vector would be
+            # silently ignored, so it is read-only -- change the areas with set_areas(R, ...)
+            a.flags.writeable = False
             return a
         return make
     return RegridderB200(M, _Lazy(fetch(0)), _Lazy(fetch(1)), _Lazy(lambda: np.zeros(n_dst)),
@@ -390,6 +449,14 @@ def Regridder(dst, src, *, manifold: Optional[int] = None, normalize: bool = Fal
     L = _lib.lib()
     out = C.c_void_p()
     keep = []
+    if stream is None:
+        # device-resident vertices: build on torch's current stream, after the kernels that wrote them
+        for g in (gd, gs):
+            if isinstance(g, Grid) and _is_torch(g.verts) and g.verts.is_cuda:
+                stream = torch_stream_ptr(g.verts.device)
+                break
+    elif stream == 0:
+        stream = CUDA_STREAM_LEGACY
     if isinstance(gd, GridSpec) or isinstance(gs, GridSpec):
         if intersection_operator is not None:
             gd = gd.materialize() if isinstance(gd, GridSpec) else gd
@@ -398,13 +465,20 @@ def Regridder(dst, src, *, manifold: Optional[int] = None, normalize: bool = Fal
             o = _make_options(mf, normalize, radius, device, area_threshold, build_transpose, keep_candidates, stream)
             dd, ds = _grid_struct(gd, keep), _grid_struct(gs, keep)
             _lib.check(L.crg_build_grids(C.byref(o), C.byref(dd), C.byref(ds), C.byref(out)))
-            return _wrap(out.value, gd.ncells, gs.ncells)
+            return _wrap(out.value, gd.ncells, gs.ncells, stream)
+    if mf == PLANAR and intersection_operator is None and not (_is_torch(gd.verts) or _is_torch(gs.verts)):
+        # non-convex (or > CRG_MAX_VERTS-vertex) planar cells: the reference's planar operator is Foster-Hormann
+        # (regridder.jl:87-94); here they are split into convex parts whose pair areas add up (decompose.py)
+        from .decompose import convex_parts
+        pd_, ps_ = convex_parts(gd), convex_parts(gs)
+        if pd_ is not None or ps_ is not None:
+            return _regridder_from_parts(gd, gs, pd_, ps_, normalize, radius, device, build_transpose, stream)
     cd = _cells_struct(gd, keep)
     cs = _cells_struct(gs, keep)
     if intersection_operator is None:
         o = _make_options(mf, normalize, radius, device, area_threshold, build_transpose, keep_candidates, stream)
         _lib.check(L.crg_build(C.byref(o), C.byref(cd), C.byref(cs), C.byref(out)))
-        return _wrap(out.value, gd.ncells, gs.ncells)
+        return _wrap(out.value, gd.ncells, gs.ncells, stream)
     # plugin path: device broad phase -> host operator per pair -> device assembly
     o = _make_options(mf, False, radius, device, 0.0, False, True)
     _lib.check(L.crg_build(C.byref(o), C.byref(cd), C.byref(cs), C.byref(out)))
@@ -426,6 +500,25 @@ def Regridder(dst, src, *, manifold: Optional[int] = None, normalize: bool = Fal
                                     vals.ctypes.data, tmp.dst_areas.ctypes.data, tmp.src_areas.ctypes.data,
                                     C.byref(out2)))
     return _wrap(out2.value, gd.ncells, gs.ncells)
+
+
+def _regridder_from_parts(gd, gs, parts_d, parts_s, normalize, radius, device, build_transpose, stream):
+    """Regridder of planar grids with non-convex cells from the regridder of their convex parts."""
+    pg_d, own_d = parts_d if parts_d is not None else (gd, np.arange(gd.ncells, dtype=np.int64))
+    pg_s, own_s = parts_s if parts_s is not None else (gs, np.arange(gs.ncells, dtype=np.int64))
+    P = Regridder(pg_d, pg_s, manifold=PLANAR, radius=radius, device=device, build_transpose=False, stream=stream)
+    A = P.intersections.tocsr().tocoo()
+    da = np.bincount(own_d, weights=P.dst_areas, minlength=gd.ncells)
+    sa = np.bincount(own_s, weights=P.src_areas, minlength=gs.ncells)
+    rows = np.ascontiguousarray(own_d[A.row], dtype=np.int64)
+    cols = np.ascontiguousarray(own_s[A.col], dtype=np.int64)
+    vals = np.ascontiguousarray(A.data, dtype=np.float64)
+    o = _make_options(PLANAR, normalize, radius, device, 0.0, build_transpose, False, stream)
+    out = C.c_void_p()
+    _lib.check(_lib.lib().crg_build_from_coo(C.byref(o), gd.ncells, gs.ncells, len(vals), rows.ctypes.data,
+                                             cols.ctypes.data, vals.ctypes.data, da.ctypes.data, sa.ctypes.data,
+                                             C.byref(out)))
+    return _wrap(out.value, gd.ncells, gs.ncells, stream)
 
 
 def regridder_from_coo(n_dst, n_src, dst_idx, src_idx, areas, dst_areas, src_areas, *, normalize=False,
@@ -496,6 +589,8 @@ def regrid_(dst_field, R: RegridderB200, src_field, *, dims: int = 0, normalize:
     M = R.intersections
     n_out, n_in = M.shape
     nd_s, nd_d = src_field.ndim, dst_field.ndim
+    if _is_torch(src_field) and _is_torch(dst_field) and dst_field.is_cuda:
+        M.follow_torch_stream(dst_field)
     if nd_s == 1 and nd_d == 1:
         if src_field.shape[0] != n_in or dst_field.shape[0] != n_out:
             raise DimensionMismatch(f"regridder is {n_out}x{n_in}, fields have {dst_field.shape[0]} and {src_field.shape[0]} cells")
@@ -608,6 +703,38 @@ def regrid(R: RegridderB200, src_field, **kw):
 def areas(grid, manifold: Optional[int] = None) -> np.ndarray:
     """``areas(manifold, x, tree)`` for one grid (regridder.jl:165-178), computed on the device."""
     g = as_grid(grid, manifold)
-    tiny = Grid(g.verts[:1] if g.offsets is None else g.cell(0)[None], g.manifold, None, g.radius)
+    if isinstance(g, GridSpec):                       # described grid: any one-cell partner will do
+        one = np.array([[[1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]]])
+        tiny = Grid(one, SPHERICAL, None, g.radius)
+    else:
+        first = g.verts[:1] if g.offsets is None else g.cell(0)[None]
+        if _is_torch(first):
+            first = first.cpu().numpy()
+        tiny = Grid(np.array(first, dtype=np.float64), g.manifold, None, g.radius)
     R = Regridder(g, tiny, build_transpose=False)
     return R.dst_areas
+
+
+def clip_pairs(dst, src, src_idx, dst_idx, *, manifold: Optional[int] = None, radius: Optional[float] = None,
+               device: Optional[int] = None, area_threshold: float = 0.0) -> np.ndarray:
+    """``compute_intersection_areas`` (intersection_areas.jl:4-32) with the default operator for an explicit
+    list of 0-based (src, dst) pairs, run by the kernels of the build (``crg_clip_pairs``): the area of every
+    pair (x radius^2), 0 where the pair does not survive ``area > 0``."""
+    gd, gs = as_grid(dst, manifold), as_grid(src, manifold)
+    if isinstance(gd, GridSpec):
+        gd = gd.materialize()
+    if isinstance(gs, GridSpec):
+        gs = gs.materialize()
+    if gd.manifold != gs.manifold:
+        raise ValueError(f"Destination and source manifolds must be the same. Got {gd.manifold} and {gs.manifold}.")
+    keep = []
+    cd, cs = _cells_struct(gd, keep), _cells_struct(gs, keep)
+    si = np.ascontiguousarray(src_idx, dtype=np.int64)
+    di = np.ascontiguousarray(dst_idx, dtype=np.int64)
+    if si.shape != di.shape or si.ndim != 1:
+        raise DimensionMismatch("src_idx and dst_idx must be 1-D arrays of the same length")
+    out = np.zeros(si.shape[0], dtype=np.float64)
+    o = _make_options(gd.manifold, False, gd.radius if radius is None else radius, device, area_threshold, False, False)
+    _lib.check(_lib.lib().crg_clip_pairs(C.byref(o), C.byref(cd), C.byref(cs), si.shape[0], si.ctypes.data,
+                                         di.ctypes.data, out.ctypes.data))
+    return out

@@ -145,6 +145,14 @@ int crg_build_from_coo(const crg_options *opts, int64_t n_dst, int64_t n_src, in
                        const int64_t *dst_idx, const int64_t *src_idx, const double *area,
                        const double *dst_areas, const double *src_areas, crg_regridder **out);
 
+/* compute_intersection_areas (src/regridder/intersection_areas.jl:4-32) with the default operator
+ * (regridder.jl:87-103) for an explicit list of 0-based (src, dst) cell pairs, run by the kernels of
+ * crg_build: area_out[k] = area(src[src_idx[k]] n dst[dst_idx[k]]) * radius^2, or 0 when the pair does
+ * not survive `area > threshold`.  Index and output arrays may be host or device pointers.  (The
+ * parity harness checks these per-pair values against 50-digit arithmetic.)                          */
+int crg_clip_pairs(const crg_options *opts, const crg_cells *dst, const crg_cells *src, int64_t n_pairs,
+                   const int64_t *src_idx, const int64_t *dst_idx, double *area_out);
+
 int crg_free(crg_regridder *r);
 
 int crg_dims(const crg_regridder *r, int64_t *n_dst, int64_t *n_src, int64_t *nnz);
@@ -152,6 +160,11 @@ int crg_stats(const crg_regridder *r, crg_build_stats *stats);
 
 /* Geometric cell areas (already divided by maximum(A) when normalised). Either may be NULL. */
 int crg_areas(const crg_regridder *r, double *dst_areas, double *src_areas);
+
+/* Overwrite the area vectors the fused division of crg_apply uses (regrid! divides by
+ * `regridder.dst_areas`, regrid.jl:104-118, which a user may edit in place -- masking, custom
+ * normalisation).  Either may be NULL (left as is); host or device pointers.                     */
+int crg_set_areas(crg_regridder *r, const double *dst_areas, const double *src_areas);
 
 /* R.intersections as CSC (n_dst x n_src): colptr[n_src+1], rowval[nnz], nzval[nnz], rows
  * sorted within each column.  index_base = 1 for Julia.  Host pointers only.  Any NULL is
@@ -188,7 +201,12 @@ int crg_apply_async(crg_regridder *r, int32_t transpose, int32_t divide_by_area,
                     int32_t level_fastest);
 
 /* Run the handle's work on a caller-owned cudaStream_t (e.g. torch's current stream).
- * NULL restores the handle's own stream.                                                    */
+ * NULL restores the handle's own (non-blocking) stream; the legacy default stream is named
+ * explicitly as cudaStreamLegacy ((cudaStream_t)0x1), the per-thread one as cudaStreamPerThread
+ * ((cudaStream_t)0x2).  Does not wait on the host: work already enqueued on the previous stream is
+ * ordered before what follows on the new one with an event.  The library orders its own work on the
+ * handle's stream only: producers of `src` and consumers of `dst` on OTHER streams are the caller's
+ * to order (or pass their stream here, which is what the Python/torch front end does).            */
 int crg_set_stream(crg_regridder *r, void *cuda_stream);
 int crg_synchronize(crg_regridder *r);
 

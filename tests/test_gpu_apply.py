@@ -138,8 +138,8 @@ def test_long_rows_and_empty_rows(gpu):
 
 @pytest.mark.parametrize("case", ["short", "long", "mixed", "empty_runs", "exact_chunks", "one_row"])
 def test_spmv_stream_kernel_stress(gpu, case):
-    """K7 (TMA-streamed nnz chunks of 2048): rows spanning several chunks, long segments, runs of
-    empty rows, nnz an exact multiple of the chunk, single dense row -- vs scipy on the same matrix."""
+    """K7 (SELL-32-sigma SpMV): rows far longer than a slice piece (cut slices, ticketed partial sums), long
+    segments, runs of empty rows, a matrix of exactly uniform rows, a single dense row -- vs scipy on the same matrix."""
     import scipy.sparse as sp
     from crg_b200.regridder import regridder_from_coo
     rng = np.random.default_rng(hash(case) % 2 ** 31)
@@ -177,3 +177,60 @@ def test_spmv_stream_kernel_stress(gpu, case):
     for _ in range(3):
         y3 = np.zeros(n_dst); regrid_(y3, R, x)
         assert np.array_equal(y3, y)
+
+
+def test_torch_default_stream_ordering(gpu):
+    """CUDA-tensor applies run on torch's CURRENT stream -- also when that is the legacy
+    default stream, which torch reports as handle 0 -- so they are ordered after the kernels that produce
+    the inputs and before the consumers of the outputs, without any explicit stream plumbing."""
+    import torch
+    dst, src = grids.lonlat_grid(720, 360), grids.healpix_grid(128, "ring")
+    R = Regridder(dst, src)                          # host vertices: the handle starts on the library stream
+    A = R.intersections.tocsr()
+    rng = np.random.default_rng(8)
+    x = rng.random(src.ncells)
+    ref = (A @ x) / R.dst_areas
+    big = torch.ones(64 << 20, device="cuda")        # a long-running producer in front of the input
+    for use_side_stream in (False, True):
+        ctx = torch.cuda.stream(torch.cuda.Stream()) if use_side_stream else torch.cuda.stream(torch.cuda.default_stream())
+        with ctx:
+            for _ in range(3):
+                xd = torch.zeros(src.ncells, dtype=torch.float64, device="cuda")
+                yd = torch.full((dst.ncells,), float("nan"), dtype=torch.float64, device="cuda")
+                big.mul_(1.0000001); big.mul_(0.9999999)         # keep the stream busy ...
+                xd.copy_(torch.from_numpy(x).cuda(), non_blocking=True)   # ... then produce the input on it
+                regrid_(yd, R, xd, asynchronous=True)
+                out = yd * 2.0                                    # consumer on the same stream
+                got = out.cpu().numpy() / 2.0
+                assert np.allclose(got, ref, rtol=1e-13, atol=0)
+    assert R.intersections._h.stream is not None      # the handle followed torch's stream
+    # dropping the handle while an asynchronous apply may still be in flight is safe (destroy waits on the stream)
+    yd = torch.zeros(dst.ncells, dtype=torch.float64, device="cuda")
+    for _ in range(5):
+        R2 = Regridder(dst, src)
+        regrid_(yd, R2, torch.from_numpy(x).cuda(), asynchronous=True)
+        del R2
+    torch.cuda.synchronize()
+    assert np.allclose(yd.cpu().numpy(), ref, rtol=1e-13, atol=0)
+
+
+def test_set_areas_reaches_the_device(gpu):
+    """regrid! divides by `regridder.dst_areas` (regrid.jl:104-118), which users may replace (masking, custom
+    normalisation): the host vectors are read-only views and set_areas pushes new values to the device."""
+    from crg_b200.regridder import set_areas
+    dst, src = grids.lonlat_grid(36, 18), grids.healpix_grid(8, "ring")
+    R = Regridder(dst, src)
+    A = R.intersections.tocsr()
+    x = np.random.default_rng(2).random(src.ncells)
+    with pytest.raises(ValueError):
+        R.dst_areas[0] = 1.0                         # read-only: an in-place edit would be silently ignored
+    new = R.dst_areas * np.linspace(1, 2, dst.ncells)
+    set_areas(R, dst_areas=new)
+    assert np.array_equal(R.dst_areas, new) and transpose(R).src_areas is R.dst_areas
+    y = np.zeros(dst.ncells); regrid_(y, R, x)
+    assert np.allclose(y, (A @ x) / new, rtol=1e-13)
+    T = transpose(R)
+    news = R.src_areas * 3.0
+    set_areas(T, dst_areas=news)                     # transpose(R).dst_areas is R.src_areas
+    xb = np.zeros(src.ncells); regrid_(xb, T, y)
+    assert np.allclose(xb, (A.T @ y) / news, rtol=1e-13)

@@ -427,3 +427,76 @@ def test_one_by_one_and_two_by_one(gpu):
     assert np.allclose(R2.intersections.tocsc().toarray(), [[0.5, 0.5]])
     y = np.zeros(1); regrid_(y, R2, np.array([1.0, 3.0])); assert abs(y[0] - 2.0) < 1e-15
     xb = np.zeros(2); regrid_(xb, transpose(R2), np.array([2.0])); assert np.allclose(xb, [2.0, 2.0])
+
+
+def test_nonconvex_cells_are_detected_not_silently_clipped(gpu):
+    """the device clip is convex-convex; the C ABI refuses non-convex rings."""
+    import ctypes as C
+    from crg_b200.regridder import _cells_struct, _make_options
+    L = np.array([(0, 0), (2, 0), (2, 1), (1, 1), (1, 2), (0, 2)], dtype=float)
+    sq = np.array([(0, 0), (2, 0), (2, 2), (0, 2), (0, 2), (0, 2)], dtype=float)      # convex, padded with a repeated vertex
+    g_bad = grids.Grid(np.stack([L, sq]), grids.PLANAR)
+    g_ok = grids.planar_unit_square_grid(2, 2)
+    keep = []
+    o = _make_options(grids.PLANAR, False, 1.0, None, 0.0, True, False)
+    out = C.c_void_p()
+    rc = _lib.lib().crg_build(C.byref(o), C.byref(_cells_struct(g_bad, keep)), C.byref(_cells_struct(g_ok, keep)), C.byref(out))
+    assert rc == _lib.CRG_ERR_UNSUPPORTED and b"not convex" in _lib.lib().crg_last_error()
+    rc = _lib.lib().crg_build(C.byref(o), C.byref(_cells_struct(g_ok, keep)), C.byref(_cells_struct(g_bad, keep)), C.byref(out))
+    assert rc == _lib.CRG_ERR_UNSUPPORTED
+    # a non-convex spherical quad (one corner pushed inside) is refused as well
+    q = grids.lonlat_grid(8, 4).verts.copy()
+    q[5, 2] = (0.8 * q[5, 0] + 0.1 * q[5, 1] + 0.1 * q[5, 3]); q[5, 2] /= np.linalg.norm(q[5, 2])
+    with pytest.raises(_lib.CrgError) as ei:
+        Regridder(grids.Grid(q, grids.SPHERICAL), grids.healpix_grid(2, "ring"))
+    assert ei.value.code == _lib.CRG_ERR_UNSUPPORTED
+
+
+def test_planar_nonconvex_polygons_through_convex_parts(gpu):
+    """The reference's planar operator is Foster-Hormann (regridder.jl:87-94): non-convex simple polygons are
+    legal input.  The front end splits them into convex parts and sums the part pairs (decompose.py)."""
+    L = [(0, 0), (2, 0), (2, 1), (1, 1), (1, 2), (0, 2)]                       # area 3
+    U = [(0, 0), (3, 0), (3, 3), (2, 3), (2, 1), (1, 1), (1, 3), (0, 3)]       # area 7, 8 vertices, two notches
+    star = [(2 + np.cos(a) * (1.5 if i % 2 == 0 else .5), 2 + np.sin(a) * (1.5 if i % 2 == 0 else .5))
+            for i, a in enumerate(np.linspace(0, 2 * np.pi, 11)[:-1])]          # 10 vertices > CRG_MAX_VERTS
+    dst = grids.polygons_grid([L, U[::-1], star])
+    src = grids.planar_regular_grid(np.linspace(-1, 4, 21), np.linspace(-1, 4, 21))   # 0.25 squares covering everything
+    R = Regridder(dst, src)
+    A = R.intersections.toarray()
+    shoelace = lambda p: 0.5 * abs(sum(p[i][0] * p[(i + 1) % len(p)][1] - p[(i + 1) % len(p)][0] * p[i][1] for i in range(len(p))))
+    want = np.array([shoelace(L), shoelace(U), shoelace(star)])
+    assert np.allclose(R.dst_areas, want, rtol=1e-14)
+    assert np.allclose(A.sum(1), want, rtol=1e-13)              # the squares tile the plane: row sums = polygon areas
+    assert np.allclose(R.src_areas, 0.0625)
+    # a unit square inside the notch of U does not touch it; one inside the arm is fully covered
+    sq = lambda x, y: [(x, y), (x + 1, y), (x + 1, y + 1), (x, y + 1)]
+    R2 = Regridder(grids.polygons_grid([U]), grids.polygons_grid([sq(1, 1.5), sq(0, 1.5), sq(0.5, 0.5)]))
+    assert np.allclose(R2.intersections.toarray(), [[0.0, 1.0, 0.75]], atol=1e-15)
+    # exact arithmetic case against the oracle on the convex parts
+    y = np.zeros(3); regrid_(y, R, np.ones(src.ncells))
+    assert np.allclose(y, 1.0, rtol=1e-13)
+
+
+def test_clip_pairs_matches_the_build_and_the_oracle(gpu):
+    """crg_clip_pairs = compute_intersection_areas (intersection_areas.jl:4-32) over a pair list."""
+    from crg_b200.regridder import clip_pairs
+    oracle = _oracle()
+    dst, src = grids.lonlat_grid(90, 45), grids.healpix_grid(16, "nested")
+    R = Regridder(dst, src, keep_candidates=True)
+    ps, pd = R.intersections.candidates()
+    a = clip_pairs(dst, src, ps, pd)
+    A = R.intersections.tocsr()
+    assert np.array_equal(a[a > 0], np.asarray(A[pd[a > 0], ps[a > 0]]).ravel())      # bit-identical to the build
+    assert (a > 0).sum() == A.nnz
+    i1, i2, oa = oracle.compute_intersection_areas(dst, src, ps, pd)
+    key = pd * src.ncells + ps
+    order = np.argsort(key)
+    want = np.zeros(len(ps)); want[order[np.searchsorted(key[order], i2 * src.ncells + i1)]] = oa
+    assert np.allclose(a, want, rtol=1e-10, atol=1e-12 * want.max())
+    # radius scaling, planar manifold, ragged cells, error paths
+    assert np.allclose(clip_pairs(dst, src, ps[:100], pd[:100], radius=3.0), 9.0 * a[:100], rtol=1e-15)
+    g1, g2 = kat_simple()
+    kk = np.array([(s, d) for d in range(4) for s in range(5)])
+    assert np.array_equal(clip_pairs(g1, g2, kk[:, 0], kk[:, 1]).reshape(4, 5), KAT_MATRIX)
+    with pytest.raises(_lib.CrgError):
+        clip_pairs(dst, src, [src.ncells], [0])

@@ -142,3 +142,17 @@ def test_against_50_digit_areas():
     assert worst < 1e-12, worst
     for c in (0, 7, 100):
         assert abs(oracle.polygon_area(1, dst.cell(c)) / highprec.polygon_area(dst.cell(c)) - 1) < 1e-13
+
+
+def test_oracle_clip_against_independent_50_digit_areas_at_bench_scale():
+    """12 600 pairs sampled from the candidate lists of BASELINE configs 5, 2 and 1 (random, polar, slivers,
+    non-overlapping, aligned, nested): the oracle's Float64 Sutherland-Hodgman + excess against an independent
+    exact-predicate / 50-digit vertex-enumeration + Girard answer (tests/golden/make_highprec_pairs.py)."""
+    from helpers import highprec_check
+    z = np.load(os.path.join(GOLDEN, "highprec_pairs.npz"))
+    got = np.array([oracle.intersection_area(1, s, d) for s, d in zip(z["src_verts"], z["dst_verts"])])
+    got = np.where(got > 0, got, 0.0)                       # `area > 0` (intersection_areas.jl:24)
+    rep = highprec_check(got, z)
+    assert rep["n_pairs"] >= 10000
+    assert rep["n_beyond_tolerance"] == 0, rep
+    assert rep["n_kept_above_tau_where_exact_is_zero"] == 0 and rep["n_dropped_where_exact_above_tau"] == 0, rep
