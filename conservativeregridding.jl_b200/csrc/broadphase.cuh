@@ -202,7 +202,7 @@ __device__ __forceinline__ bool ring_is_convex(const double *p, int n, bool cloc
         const double *u = p + DIM * e, *v = p + DIM * (e + 1 == n ? 0 : e + 1);
         double nx, ny, nz = 0.0, h0 = 0.0;
         if (DIM == 3) {
-            nx = u[1] * v[2] - u[2] * v[1]; ny = u[2] * v[0] - u[0] * v[2]; nz = u[0] * v[1] - u[1] * v[0];
+            edge_normal(u, v, nx, ny, nz);
         } else {
             nx = -(v[1] - u[1]); ny = v[0] - u[0];
             h0 = -(nx * u[0] + ny * u[1]);
@@ -220,10 +220,18 @@ __device__ __forceinline__ bool ring_is_convex(const double *p, int n, bool cloc
     return true;
 }
 
+// Single-precision "shadow" of a spherical quadrilateral for the pair classification of K3 (kernels.cuh:
+// classify_pairs_kernel): 4 vertices + 4 ORIENTED edge normals (inside >= 0 whatever the stored winding), the
+// normals taken from the FP64 cross products -- 24 floats = 96 bytes per cell.  nrm64 (destination grids):
+// the same oriented normals in FP64, 12 doubles per cell, which the cut stage clips against.
+constexpr int SHADOW_FLOATS = 24;
+
 template <int DIM>
 __global__ void __launch_bounds__(256) bp_bounds_kernel(CellsView g, float *__restrict__ diam, BPStats *st,
                                                         float big_chord, double scale, double *__restrict__ areas,
-                                                        uint8_t *__restrict__ flip, unsigned int *__restrict__ nflip) {
+                                                        uint8_t *__restrict__ flip, unsigned int *__restrict__ nflip,
+                                                        float4 *__restrict__ shadow = nullptr,
+                                                        double *__restrict__ nrm64 = nullptr) {
     __shared__ CellStage<DIM> stage;
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     // bounding box of the vertices: exact (double) in the plane, where it becomes the bin-grid domain;
@@ -244,6 +252,25 @@ __global__ void __launch_bounds__(256) bp_bounds_kernel(CellsView g, float *__re
         const float d = cell_diameter<DIM>(p, n);
         diam[c] = d;
         if (!ring_is_convex<DIM>(p, n, f, (double)d)) atomicAdd(nflip + 2, 1u);   // nflip[2..3]: non-convex cells
+        if (DIM == 3 && n == 4 && (shadow || nrm64)) {
+            const double sg = f ? -1.0 : 1.0;
+            float sh[SHADOW_FLOATS];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const double *u = p + 3 * e, *v = p + 3 * ((e + 1) & 3);
+                double nx, ny, nz;
+                edge_normal(u, v, nx, ny, nz);         // exact zero for a zero-length edge (geom.cuh)
+                nx *= sg; ny *= sg; nz *= sg;
+                sh[3 * e] = (float)u[0]; sh[3 * e + 1] = (float)u[1]; sh[3 * e + 2] = (float)u[2];
+                sh[12 + 3 * e] = (float)nx; sh[12 + 3 * e + 1] = (float)ny; sh[12 + 3 * e + 2] = (float)nz;
+                if (nrm64) { double *o = nrm64 + (size_t)c * 12 + 3 * e; o[0] = nx; o[1] = ny; o[2] = nz; }
+            }
+            if (shadow) {
+                float4 *o = shadow + (size_t)c * (SHADOW_FLOATS / 4);
+#pragma unroll
+                for (int k = 0; k < SHADOW_FLOATS / 4; ++k) o[k] = make_float4(sh[4 * k], sh[4 * k + 1], sh[4 * k + 2], sh[4 * k + 3]);
+            }
+        }
         if (DIM == 2 || d < big_chord) {
             sum = d; mx = d; cnt = 1;
             for (int i = 0; i < n; ++i)

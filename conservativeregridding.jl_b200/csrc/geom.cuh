@@ -28,6 +28,16 @@ __device__ __forceinline__ d3 cross(d3 a, d3 b) {
     return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
 
+// Normal u x v of the great circle through an edge, WITHOUT fused multiply-adds: with contraction,
+// fma(u1, v2, -rn(u2 v1)) of a zero-length edge (u == v bit for bit: the pole corners of a lon-lat cell) is the
+// rounding error of a product -- a 1e-17 vector of arbitrary direction that then "separates" or "cuts" cells --
+// unless the coordinates happen to be exact (unrotated grids).  Products rounded separately cancel exactly.
+__device__ __forceinline__ void edge_normal(const double *u, const double *v, double &nx, double &ny, double &nz) {
+    nx = __dsub_rn(__dmul_rn(u[1], v[2]), __dmul_rn(u[2], v[1]));
+    ny = __dsub_rn(__dmul_rn(u[2], v[0]), __dmul_rn(u[0], v[2]));
+    nz = __dsub_rn(__dmul_rn(u[0], v[1]), __dmul_rn(u[1], v[0]));
+}
+
 // Accumulates spherical-excess half-angles as a complex product: the triangle (a, b, c)
 // contributes the angle of z = (1 + a.b + b.c + c.a) + i a.((b-a) x (c-a)), i.e. E/2, and
 // sum of angles = angle of the product -- one atan2 per polygon instead of one per
@@ -156,8 +166,7 @@ __device__ double clip_pair_area(const CellsView &gs, int64_t s, const CellsView
         // half-space of the directed edge u -> v: inside <=> h(p) >= 0
         double nx, ny, nz = 0.0, h0 = 0.0;
         if (DIM == 3) {
-            const d3 n = cross(d3{u[0], u[1], u[2]}, d3{v[0], v[1], v[2]});
-            nx = n.x; ny = n.y; nz = n.z;
+            edge_normal(u, v, nx, ny, nz);
             if (nx == 0.0 && ny == 0.0 && nz == 0.0) continue;   // zero-length edge (pole cells)
         } else {
             const double ex = v[0] - u[0], ey = v[1] - u[1];
@@ -315,7 +324,7 @@ __device__ __forceinline__ int quad_prepass(const CellsView &gs, int64_t s, cons
         const double *u = cv[e], *v = cv[(e + 1) & 3];
         double nx, ny, nz = 0.0, h0 = 0.0;
         if (DIM == 3) {
-            nx = u[1] * v[2] - u[2] * v[1]; ny = u[2] * v[0] - u[0] * v[2]; nz = u[0] * v[1] - u[1] * v[0];
+            edge_normal(u, v, nx, ny, nz);
         } else {
             nx = -(v[1] - u[1]); ny = v[0] - u[0];
             h0 = -(nx * u[0] + ny * u[1]);
@@ -336,12 +345,14 @@ __device__ __forceinline__ int quad_prepass(const CellsView &gs, int64_t s, cons
 
 // Area of subject ∩ clip given the set of cutting clip edges (quad_prepass).  A lane only visits ITS
 // cutting edges, so the lanes of a warp meet in the cut code even when different edges cut them.
-template <int DIM, int NT>
+// NRM = true (sphere): the clip cell's ORIENTED edge normals come precomputed (bp_bounds_kernel: nrm64, 12
+// doubles per cell) -- no clip-vertex loads, no cross products, no orientation fix-up in the cut loop.
+template <int DIM, int NT, bool NRM = false>
 __device__ double quad_cut_area(const CellsView &gs, int64_t s, const CellsView &gc, int64_t c, uint32_t cut,
-                                double *smem /* QUAD_SLOTS * DIM * NT doubles */) {
+                                double *smem /* QUAD_SLOTS * DIM * NT doubles */, const double *__restrict__ nrm64 = nullptr) {
     PointTable<DIM, NT> tab{smem + threadIdx.x};
-    const double *cbase = gc.verts + c * 4 * DIM;
-    const double sc = (gc.flip && gc.flip[c]) ? -1.0 : 1.0;        // clockwise clip cell: normals negated
+    const double *cbase = NRM ? nrm64 + c * 12 : gc.verts + c * 4 * DIM;
+    const double sc = NRM ? 1.0 : ((gc.flip && gc.flip[c]) ? -1.0 : 1.0);   // clockwise clip cell: normals negated
     const double ss = (gs.flip && gs.flip[s]) ? -1.0 : 1.0;        // clockwise subject: area negated
     {
         double sv[4][DIM];
@@ -358,11 +369,17 @@ __device__ double quad_cut_area(const CellsView &gs, int64_t s, const CellsView 
         cut &= cut - 1u;
         const int iu = e, iv = (e + 1) & 3;
         double u[3] = {0.0, 0.0, 0.0}, v[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-        for (int k = 0; k < DIM; ++k) { u[k] = __ldg(cbase + iu * DIM + k); v[k] = __ldg(cbase + iv * DIM + k); }
         double nx, ny, nz = 0.0, h0 = 0.0;
-        if (DIM == 3) {
-            nx = sc * (u[1] * v[2] - u[2] * v[1]); ny = sc * (u[2] * v[0] - u[0] * v[2]); nz = sc * (u[0] * v[1] - u[1] * v[0]);
+        if (NRM) {
+            nx = __ldg(cbase + 3 * e); ny = __ldg(cbase + 3 * e + 1); nz = __ldg(cbase + 3 * e + 2);
+        } else {
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) { u[k] = __ldg(cbase + iu * DIM + k); v[k] = __ldg(cbase + iv * DIM + k); }
+        }
+        if (NRM) {
+        } else if (DIM == 3) {
+            edge_normal(u, v, nx, ny, nz);
+            nx *= sc; ny *= sc; nz *= sc;
         } else {
             nx = -sc * (v[1] - u[1]); ny = sc * (v[0] - u[0]);
             h0 = -(nx * u[0] + ny * u[1]);

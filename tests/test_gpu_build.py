@@ -234,10 +234,17 @@ def test_ragged_clockwise_and_degenerate_cells(gpu):
     assert abs(A - B).max() < 1e-15
     A2 = Regridder(s, cw).intersections.tocsc()
     assert abs(A2 - A.T).max() < 1e-15
-    # too many vertices is reported, not truncated
+    # too many vertices: planar rings are split into convex parts by the front end (decompose.py) ...
     big = grids.polygons_grid([poly(0, 0, 12, 1.0, False), poly(0, 0, 3, 1.0, False)])
+    Rb = Regridder(big, src)
+    Ob = oracle.build_regridder(big, src)
+    assert abs(Rb.intersections.tocsc() - Ob.tocsc()).max() < 1e-13 and np.allclose(Rb.dst_areas, Ob.dst_areas, rtol=1e-13)
+    # ... on the sphere (and at the C ABI) they are reported, not truncated
+    t = np.linspace(0, 2 * np.pi, 13)[:-1]
+    ring12 = np.stack([0.1 * np.cos(t), 0.1 * np.sin(t), np.ones(12)], axis=1)
+    ring12 /= np.linalg.norm(ring12, axis=1)[:, None]
     with pytest.raises(_lib.CrgError) as e:
-        Regridder(big, src)
+        Regridder(grids.polygons_grid([ring12, ring12[:3]], grids.SPHERICAL), grids.healpix_grid(1, "ring"))
     assert e.value.code == _lib.CRG_ERR_UNSUPPORTED
 
 
@@ -331,6 +338,11 @@ def test_rotated_polar_and_identical_grids(gpu):
     A = R.intersections.tocsr()
     assert np.allclose(np.asarray(A.sum(1)).ravel(), R.dst_areas, rtol=1.5e-8)
     assert np.allclose(np.asarray(A.sum(0)).ravel(), R.src_areas, rtol=1.5e-8)
+    # ... and with the roles swapped: the rotated pole corners (zero-length edges whose coordinates are not exact)
+    # now belong to the CLIP cells
+    R = Regridder(src, dst)
+    O = oracle.build_regridder(src, dst, nthreads=oracle.max_threads())
+    compare_matrices(R.intersections.tocsc(), O.tocsc(), O.dst_areas, O.src_areas)
     # polar caps as octagons that contain the pole + bands of quads (ragged: offsets path)
     def cap_grid(nlon, lats):
         polys = []
@@ -446,7 +458,7 @@ def test_nonconvex_cells_are_detected_not_silently_clipped(gpu):
     assert rc == _lib.CRG_ERR_UNSUPPORTED
     # a non-convex spherical quad (one corner pushed inside) is refused as well
     q = grids.lonlat_grid(8, 4).verts.copy()
-    q[5, 2] = (0.8 * q[5, 0] + 0.1 * q[5, 1] + 0.1 * q[5, 3]); q[5, 2] /= np.linalg.norm(q[5, 2])
+    q[13, 2] = (0.8 * q[13, 0] + 0.1 * q[13, 1] + 0.1 * q[13, 3]); q[13, 2] /= np.linalg.norm(q[13, 2])   # (a mid-latitude cell)
     with pytest.raises(_lib.CrgError) as ei:
         Regridder(grids.Grid(q, grids.SPHERICAL), grids.healpix_grid(2, "ring"))
     assert ei.value.code == _lib.CRG_ERR_UNSUPPORTED
