@@ -14,7 +14,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
-LIB_PATH = os.path.join(CSRC, "libcrgb200.so")
+# (CRG_LIB / CRG_NVCC_EXTRA: experiment hooks -- a variant of the library built with extra -D flags, see scripts/variants.py)
+LIB_PATH = os.environ.get("CRG_LIB") or os.path.join(CSRC, "libcrgb200.so")
 SOURCES = ["crg_b200.cu"]
 HEADERS = ["common.cuh", "scan.cuh", "sort.cuh", "geom.cuh", "gridgen.cuh", "broadphase.cuh", "kernels.cuh", "sell.cuh"]
 
@@ -87,7 +88,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get("CRG_NVCC_EXTRA", "").split()
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-I", INCLUDE, "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(CSRC, "build.log"), "w") as f:

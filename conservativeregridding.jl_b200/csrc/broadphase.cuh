@@ -197,7 +197,11 @@ __device__ __forceinline__ const double *stage_cell(const CellsView &g, int64_t 
 // side of every edge, up to round-off: h_e(w) * orientation >= -tol * |n_e| * diameter.
 template <int DIM>
 __device__ __forceinline__ bool ring_is_convex(const double *p, int n, bool clockwise, double diam) {
+    if (n <= 3) return true;
     const double sg = clockwise ? -1.0 : 1.0;
+    // A quadrilateral is convex iff its four turns have the same sign: vertex e + 2 against edge e is enough
+    // (4 tests instead of 16); longer rings are tested vertex by vertex (same-sign turns could wind twice).
+    const int ntest = n == 4 ? 1 : n;
     for (int e = 0; e < n; ++e) {
         const double *u = p + DIM * e, *v = p + DIM * (e + 1 == n ? 0 : e + 1);
         double nx, ny, nz = 0.0, h0 = 0.0;
@@ -207,11 +211,13 @@ __device__ __forceinline__ bool ring_is_convex(const double *p, int n, bool cloc
             nx = -(v[1] - u[1]); ny = v[0] - u[0];
             h0 = -(nx * u[0] + ny * u[1]);
         }
-        // + the round-off of h itself: ~eps for unit vectors, ~eps |n| max|coordinate| in the plane
-        const double nn = sqrt(nx * nx + ny * ny + nz * nz);
+        // tolerance: 1e-9 of the cell size + the round-off of h itself (~eps for unit vectors, ~eps |n| max|coordinate|
+        // in the plane); the length of n in single precision is plenty for that
+        const double nn = (double)sqrtf((float)(nx * nx + ny * ny + nz * nz)) * 1.000001;
         const double tol = DIM == 3 ? 1e-9 * nn * diam + 1e-14
                                     : nn * (1e-9 * diam + 1e-14 * (fabs(u[0]) + fabs(u[1]) + fabs(v[0]) + fabs(v[1])));
-        for (int i = 0; i < n; ++i) {
+        for (int t = 0; t < ntest; ++t) {
+            const int i = n == 4 ? ((e + 2) & 3) : t;
             const double *w = p + DIM * i;
             const double h = DIM == 3 ? nx * w[0] + ny * w[1] + nz * w[2] : nx * w[0] + ny * w[1] + h0;
             if (sg * h < -tol) return false;
@@ -220,18 +226,10 @@ __device__ __forceinline__ bool ring_is_convex(const double *p, int n, bool cloc
     return true;
 }
 
-// Single-precision "shadow" of a spherical quadrilateral for the pair classification of K3 (kernels.cuh:
-// classify_pairs_kernel): 4 vertices + 4 ORIENTED edge normals (inside >= 0 whatever the stored winding), the
-// normals taken from the FP64 cross products -- 24 floats = 96 bytes per cell.  nrm64 (destination grids):
-// the same oriented normals in FP64, 12 doubles per cell, which the cut stage clips against.
-constexpr int SHADOW_FLOATS = 24;
-
 template <int DIM>
 __global__ void __launch_bounds__(256) bp_bounds_kernel(CellsView g, float *__restrict__ diam, BPStats *st,
                                                         float big_chord, double scale, double *__restrict__ areas,
-                                                        uint8_t *__restrict__ flip, unsigned int *__restrict__ nflip,
-                                                        float4 *__restrict__ shadow = nullptr,
-                                                        double *__restrict__ nrm64 = nullptr) {
+                                                        uint8_t *__restrict__ flip, unsigned int *__restrict__ nflip) {
     __shared__ CellStage<DIM> stage;
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     // bounding box of the vertices: exact (double) in the plane, where it becomes the bin-grid domain;
@@ -252,25 +250,6 @@ __global__ void __launch_bounds__(256) bp_bounds_kernel(CellsView g, float *__re
         const float d = cell_diameter<DIM>(p, n);
         diam[c] = d;
         if (!ring_is_convex<DIM>(p, n, f, (double)d)) atomicAdd(nflip + 2, 1u);   // nflip[2..3]: non-convex cells
-        if (DIM == 3 && n == 4 && (shadow || nrm64)) {
-            const double sg = f ? -1.0 : 1.0;
-            float sh[SHADOW_FLOATS];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const double *u = p + 3 * e, *v = p + 3 * ((e + 1) & 3);
-                double nx, ny, nz;
-                edge_normal(u, v, nx, ny, nz);         // exact zero for a zero-length edge (geom.cuh)
-                nx *= sg; ny *= sg; nz *= sg;
-                sh[3 * e] = (float)u[0]; sh[3 * e + 1] = (float)u[1]; sh[3 * e + 2] = (float)u[2];
-                sh[12 + 3 * e] = (float)nx; sh[12 + 3 * e + 1] = (float)ny; sh[12 + 3 * e + 2] = (float)nz;
-                if (nrm64) { double *o = nrm64 + (size_t)c * 12 + 3 * e; o[0] = nx; o[1] = ny; o[2] = nz; }
-            }
-            if (shadow) {
-                float4 *o = shadow + (size_t)c * (SHADOW_FLOATS / 4);
-#pragma unroll
-                for (int k = 0; k < SHADOW_FLOATS / 4; ++k) o[k] = make_float4(sh[4 * k], sh[4 * k + 1], sh[4 * k + 2], sh[4 * k + 3]);
-            }
-        }
         if (DIM == 2 || d < big_chord) {
             sum = d; mx = d; cnt = 1;
             for (int i = 0; i < n; ++i)

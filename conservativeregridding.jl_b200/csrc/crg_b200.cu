@@ -544,41 +544,16 @@ static int do_normalize(crg_regridder *R) {
 
 static int device_side_stream(int dev, cudaStream_t *out);
 
-// Single-precision shadows + FP64 normals of spherical quadrilateral grids (written by bp_bounds_kernel, read by
-// the two-kernel clip); empty when the grids do not qualify.
-struct ClipAux {
-    DevBuf<float4> shd_d, shd_s;
-    DevBuf<double> nrm64_d;
-    bool on = false;
-};
-
-static bool quad_grids(const CellsView &gdv, const CellsView &gsv, bool fixed, int nv_dst, int nv_src) {
-    return fixed && nv_dst == 4 && nv_src == 4 && ((uintptr_t)gdv.verts % 16 == 0) && ((uintptr_t)gsv.verts % 16 == 0);
-}
-
-template <int DIM>
-static int alloc_clip_aux(ClipAux &aux, const CellsView &gdv, const CellsView &gsv, bool fixed, int nv_dst, int nv_src,
-                          cudaStream_t st) {
-    static const int mode = getenv("CRG_CLIP_MODE") ? atoi(getenv("CRG_CLIP_MODE")) : 1;
-    static const bool allow_quad = !(getenv("CRG_CLIP_QUAD") && atoi(getenv("CRG_CLIP_QUAD")) == 0);
-    aux.on = DIM == 3 && mode == 1 && allow_quad && quad_grids(gdv, gsv, fixed, nv_dst, nv_src) && gdv.ncells > 0 && gsv.ncells > 0;
-    if (!aux.on) return CRG_OK;
-    CRG_TRY(aux.shd_d.alloc_tmp((size_t)gdv.ncells * (SHADOW_FLOATS / 4), st));
-    CRG_TRY(aux.shd_s.alloc_tmp((size_t)gsv.ncells * (SHADOW_FLOATS / 4), st));
-    CRG_TRY(aux.nrm64_d.alloc_tmp((size_t)gdv.ncells * 12, st));
-    return CRG_OK;
-}
-
 // K3 launcher: dense areas of `n_cand` (src, dst) pairs + survivor counts per CLIP_TILE pairs (kernels.cuh).
-// Spherical quadrilateral grids take the classify + cut-jobs pair, planar quadrilaterals the symbolic-polygon
-// kernel with in-kernel queues, everything else the general kernel.
+// Quadrilateral grids take the symbolic-polygon kernel with in-kernel queues, everything else the general one.
 template <int DIM>
 static int launch_clip(const CellsView &gdv, const CellsView &gsv, bool fixed, int nv_dst, int nv_src, const int2 *pairs,
                        int64_t n_cand, double thresh, const double *unit_src_areas, double *pair_area,
-                       uint32_t *tile_count, const ClipAux &aux, int device, cudaStream_t st) {
+                       uint32_t *tile_count, cudaStream_t st) {
     static const bool allow_quad = !(getenv("CRG_CLIP_QUAD") && atoi(getenv("CRG_CLIP_QUAD")) == 0);
     const bool fixed4 = fixed && nv_dst <= 4 && nv_src <= 4;
-    const bool quad = allow_quad && quad_grids(gdv, gsv, fixed, nv_dst, nv_src);
+    const bool quad = allow_quad && fixed4 && nv_dst == 4 && nv_src == 4 && ((uintptr_t)gdv.verts % 16 == 0) &&
+                      ((uintptr_t)gsv.verts % 16 == 0);
 #define CRG_CLIP(NT_, MW_)                                                                                            \
     do {                                                                                                              \
         const size_t smem = sizeof(double) * 2 * MW_ * DIM * NT_;                                                     \
@@ -586,29 +561,7 @@ static int launch_clip(const CellsView &gdv, const CellsView &gsv, bool fixed, i
         CRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
         kern<<<ceil_div(n_cand, NT_), NT_, smem, st>>>(gdv, gsv, pairs, n_cand, thresh, pair_area, tile_count);       \
     } while (0)
-    if (quad && aux.on && DIM == 3 && n_cand < ((int64_t)1 << CLS_IDX_BITS)) {
-        DevBuf<uint32_t> jobs, job_count;
-        CRG_TRY(jobs.alloc_tmp((size_t)n_cand, st));
-        CRG_TRY(job_count.alloc_tmp(2, st));
-        CRG_CUDA(cudaMemsetAsync(job_count.p, 0, 2 * sizeof(uint32_t), st));
-        classify_pairs_kernel<512><<<ceil_div(n_cand, 512), 512, 0, st>>>(gdv, gsv, aux.shd_d.p, aux.shd_s.p, pairs, n_cand, thresh,
-                                                                        unit_src_areas, pair_area, tile_count, jobs.p,
-                                                                        job_count.p);
-        CRG_LAUNCH_CHECK();
-        constexpr int NT = 128;
-        const size_t smem = sizeof(double) * QUAD_SLOTS * 3 * NT;
-        auto kern = cut_jobs_kernel<NT>;
-        static int grid_cache[64];
-        if (!grid_cache[device & 63]) {
-            CRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int n_sm = 0, occ = 0;
-            CRG_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
-            CRG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
-            grid_cache[device & 63] = n_sm * (occ > 0 ? occ : 1);
-        }
-        const int grid = (int)std::min<int64_t>(grid_cache[device & 63], ceil_div(n_cand, NT));
-        kern<<<grid, NT, smem, st>>>(gdv, gsv, aux.nrm64_d.p, pairs, n_cand, thresh, jobs.p, job_count.p, pair_area, tile_count);
-    } else if (quad) {
+    if (quad) {
         constexpr int NT = 128;
         const size_t smem = sizeof(double) * QUAD_SLOTS * DIM * NT;
         auto kern = clip_quad_kernel<DIM, NT>;
@@ -662,10 +615,8 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     CRG_CUDA(cudaMemcpyAsync(dstats.p, hst, sizeof(hst), cudaMemcpyHostToDevice, st));
     const double big_chord = 2.0 * std::sin(BP_BIG_ANGLE / 2.0);
     // (the views' flip pointers are still null here: the kernel sees the cells as stored)
-    ClipAux aux;
-    CRG_TRY((alloc_clip_aux<DIM>(aux, gd.view, gs.view, !dst->offsets && !src->offsets, dst->nv, src->nv, st)));
-    if (nd) { bp_bounds_kernel<DIM><<<ceil_div(nd, 256), 256, 0, st>>>(gd.view, gd.diam.p, dstats.p, (float)big_chord, r2, R->dst_areas.p, gd.flip.p, nflip.p, aux.shd_d.p, aux.nrm64_d.p); CRG_LAUNCH_CHECK(); }
-    if (ns) { bp_bounds_kernel<DIM><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, gs.diam.p, dstats.p + 1, (float)big_chord, r2, R->src_areas.p, gs.flip.p, nflip.p + 1, aux.shd_s.p, nullptr); CRG_LAUNCH_CHECK(); }
+    if (nd) { bp_bounds_kernel<DIM><<<ceil_div(nd, 256), 256, 0, st>>>(gd.view, gd.diam.p, dstats.p, (float)big_chord, r2, R->dst_areas.p, gd.flip.p, nflip.p); CRG_LAUNCH_CHECK(); }
+    if (ns) { bp_bounds_kernel<DIM><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, gs.diam.p, dstats.p + 1, (float)big_chord, r2, R->src_areas.p, gs.flip.p, nflip.p + 1); CRG_LAUNCH_CHECK(); }
     gd.view.flip = gd.flip.p;
     gs.view.flip = gs.flip.p;
     unsigned int h_nflip[4] = {0, 0, 0, 0};
@@ -838,7 +789,7 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
         CRG_CUDA(cudaMemsetAsync(tile_count.p, 0, sizeof(uint32_t) * ((size_t)ntiles + 1), st));
         CRG_TRY((launch_clip<DIM>(gd.view, gs.view, !dst->offsets && !src->offsets, dst->nv, src->nv, pairs.p, n_cand,
                                   R->opts.area_threshold, r2 == 1.0 ? R->src_areas.p : nullptr, pair_area.p,
-                                  tile_count.p, aux, R->device, st)));
+                                  tile_count.p, st)));
         CRG_TRY((exclusive_scan<uint32_t, uint32_t>(tile_count.p, ntiles, tile_count.p, st)));
         CRG_CUDA(cudaMemcpyAsync(&h_keep, tile_count.p + ntiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CRG_CUDA(cudaStreamSynchronize(st));
@@ -908,10 +859,8 @@ static int clip_pairs_impl(const crg_options *opts, const crg_cells *dst, const 
     CRG_TRY(dstats.alloc_tmp(2, st));
     CRG_CUDA(cudaMemsetAsync(nflip.p, 0, 4 * sizeof(unsigned int), st));
     CRG_CUDA(cudaMemsetAsync(dstats.p, 0, 2 * sizeof(BPStats), st));
-    ClipAux aux;
-    CRG_TRY((alloc_clip_aux<DIM>(aux, gd.view, gs.view, !dst->offsets && !src->offsets, dst->nv, src->nv, st)));
-    if (nd) { bp_bounds_kernel<DIM><<<ceil_div(nd, 256), 256, 0, st>>>(gd.view, gd.diam.p, dstats.p, 1e30f, 1.0, a_dst.p, gd.flip.p, nflip.p, aux.shd_d.p, aux.nrm64_d.p); CRG_LAUNCH_CHECK(); }
-    if (ns) { bp_bounds_kernel<DIM><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, gs.diam.p, dstats.p + 1, 1e30f, 1.0, a_src.p, gs.flip.p, nflip.p + 1, aux.shd_s.p, nullptr); CRG_LAUNCH_CHECK(); }
+    if (nd) { bp_bounds_kernel<DIM><<<ceil_div(nd, 256), 256, 0, st>>>(gd.view, gd.diam.p, dstats.p, 1e30f, 1.0, a_dst.p, gd.flip.p, nflip.p); CRG_LAUNCH_CHECK(); }
+    if (ns) { bp_bounds_kernel<DIM><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, gs.diam.p, dstats.p + 1, 1e30f, 1.0, a_src.p, gs.flip.p, nflip.p + 1); CRG_LAUNCH_CHECK(); }
     gd.view.flip = gd.flip.p;
     gs.view.flip = gs.flip.p;
     DevBuf<int64_t> di, si;
@@ -941,7 +890,7 @@ static int clip_pairs_impl(const crg_options *opts, const crg_cells *dst, const 
     if (h_nflip[2] || h_nflip[3])
         return set_error(CRG_ERR_UNSUPPORTED, "%u destination and %u source cells are not convex", h_nflip[2], h_nflip[3]);
     CRG_TRY((launch_clip<DIM>(gd.view, gs.view, !dst->offsets && !src->offsets, dst->nv, src->nv, pairs.p, n_pairs,
-                              opts->area_threshold, a_src.p, pair_area.p, tile_count.p, aux, dev, st)));
+                              opts->area_threshold, a_src.p, pair_area.p, tile_count.p, st)));
     const double r2 = DIM == 3 ? opts->radius * opts->radius : 1.0;
     if (r2 != 1.0) { scale_kernel<<<ceil_div(n_pairs, 256), 256, 0, st>>>(pair_area.p, n_pairs, r2); CRG_LAUNCH_CHECK(); }
     CRG_CUDA(cudaMemcpyAsync(area_out, pair_area.p, sizeof(double) * (size_t)n_pairs, cudaMemcpyDefault, st));

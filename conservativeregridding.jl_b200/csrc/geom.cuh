@@ -345,14 +345,12 @@ __device__ __forceinline__ int quad_prepass(const CellsView &gs, int64_t s, cons
 
 // Area of subject ∩ clip given the set of cutting clip edges (quad_prepass).  A lane only visits ITS
 // cutting edges, so the lanes of a warp meet in the cut code even when different edges cut them.
-// NRM = true (sphere): the clip cell's ORIENTED edge normals come precomputed (bp_bounds_kernel: nrm64, 12
-// doubles per cell) -- no clip-vertex loads, no cross products, no orientation fix-up in the cut loop.
-template <int DIM, int NT, bool NRM = false>
+template <int DIM, int NT>
 __device__ double quad_cut_area(const CellsView &gs, int64_t s, const CellsView &gc, int64_t c, uint32_t cut,
-                                double *smem /* QUAD_SLOTS * DIM * NT doubles */, const double *__restrict__ nrm64 = nullptr) {
+                                double *smem /* QUAD_SLOTS * DIM * NT doubles */) {
     PointTable<DIM, NT> tab{smem + threadIdx.x};
-    const double *cbase = NRM ? nrm64 + c * 12 : gc.verts + c * 4 * DIM;
-    const double sc = NRM ? 1.0 : ((gc.flip && gc.flip[c]) ? -1.0 : 1.0);   // clockwise clip cell: normals negated
+    const double *cbase = gc.verts + c * 4 * DIM;
+    const double sc = (gc.flip && gc.flip[c]) ? -1.0 : 1.0;        // clockwise clip cell: normals negated
     const double ss = (gs.flip && gs.flip[s]) ? -1.0 : 1.0;        // clockwise subject: area negated
     {
         double sv[4][DIM];
@@ -369,15 +367,10 @@ __device__ double quad_cut_area(const CellsView &gs, int64_t s, const CellsView 
         cut &= cut - 1u;
         const int iu = e, iv = (e + 1) & 3;
         double u[3] = {0.0, 0.0, 0.0}, v[3] = {0.0, 0.0, 0.0};
-        double nx, ny, nz = 0.0, h0 = 0.0;
-        if (NRM) {
-            nx = __ldg(cbase + 3 * e); ny = __ldg(cbase + 3 * e + 1); nz = __ldg(cbase + 3 * e + 2);
-        } else {
 #pragma unroll
-            for (int k = 0; k < DIM; ++k) { u[k] = __ldg(cbase + iu * DIM + k); v[k] = __ldg(cbase + iv * DIM + k); }
-        }
-        if (NRM) {
-        } else if (DIM == 3) {
+        for (int k = 0; k < DIM; ++k) { u[k] = __ldg(cbase + iu * DIM + k); v[k] = __ldg(cbase + iv * DIM + k); }
+        double nx, ny, nz = 0.0, h0 = 0.0;
+        if (DIM == 3) {
             edge_normal(u, v, nx, ny, nz);
             nx *= sc; ny *= sc; nz *= sc;
         } else {

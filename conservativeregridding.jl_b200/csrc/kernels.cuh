@@ -121,154 +121,6 @@ __global__ void __launch_bounds__(NT) clip_quad_kernel(CellsView gd, CellsView g
     if (lane == 0 && nz) atomicAdd(&tile_count[base / CLIP_TILE], (uint32_t)nz);
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Spherical quadrilaterals, two kernels instead of the in-kernel queues above (ncu on the r01 kernel: 40 % of
-// the stall samples were waits for the pair -> vertices load chain at 24 warps/SM, and the FP64 pipe idled
-// while a warp pre-screened):
-//   K3a classify_pairs_kernel  one thread per candidate pair, no shared memory, full occupancy: the static
-//       pre-pass in SINGLE precision on the cells' "shadows" (broadphase.cuh: 4 vertices + 4 oriented normals as
-//       floats) with a rigorous error bound -- 16 signed distances n_e . s_i; a pair is empty when one edge of
-//       either cell has the other cell's four corners certainly outside (the reverse test also removes the
-//       corner-to-corner false candidates, which used to run two full cuts to find out), untouched when all 16
-//       are certainly inside (area = the source cell's own area), otherwise a cut job with its set of cutting
-//       edges.  A distance inside the error band sends the pair through the FP64 pre-pass (quad_prepass), so
-//       the decisions are those of the FP64 code.  Jobs are appended (warp-aggregated atomics) to one buffer,
-//       single-cut jobs from the front and multi-cut jobs from the back.
-//   K3b cut_jobs_kernel  one thread per job over that buffer: every lane of every warp runs cuts + area from
-//       the first instruction, lanes of a warp have the same number of cuts (except at the class border).
-// Every pair's area is written exactly once (K3a: empty / untouched, K3b: jobs); tile counters as above.
-// ---------------------------------------------------------------------------------------------------------
-constexpr float CLS_EPS = 8.0f * 5.9604645e-8f;      // 8 * 2^-24: bound of |fl32(n) . fl32(s) - n . s| / ||n||_1, |s_k| <= 1
-constexpr int CLS_IDX_BITS = 28;                     // job = pair index | cut set << 28
-
-__device__ __forceinline__ void load12(const float4 *__restrict__ p, float (&v)[12]) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { const float4 q = __ldg(p + k); v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w; }
-}
-
-template <int NT>
-__global__ void __launch_bounds__(NT) classify_pairs_kernel(CellsView gd, CellsView gs, const float4 *__restrict__ shd_d,
-                                                            const float4 *__restrict__ shd_s, const int2 *__restrict__ pairs,
-                                                            int64_t npairs, double thresh,
-                                                            const double *__restrict__ unit_src_areas,
-                                                            double *__restrict__ area_out, uint32_t *__restrict__ tile_count,
-                                                            uint32_t *__restrict__ jobs, uint32_t *__restrict__ job_count) {
-    __shared__ uint32_t s_cnt[2], s_base[2];           // jobs of this block per class; their base in the global lists
-    const int lane = threadIdx.x & 31;
-    const int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x;
-    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
-    __syncthreads();
-    int state = -1;                                    // -1 empty, 0 untouched, else the set of cutting edges
-    bool nonzero = false;                              // a non-zero area was written here
-    if (idx < npairs) {
-        const int2 pr = pairs[idx];
-        float sv[12], dn[12];
-        load12(shd_s + (size_t)pr.x * 6, sv);          // source vertices
-        load12(shd_d + (size_t)pr.y * 6 + 3, dn);      // destination normals (oriented: inside >= 0)
-        bool empty = false, unsure = false;
-        uint32_t cut = 0;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float nx = dn[3 * e], ny = dn[3 * e + 1], nz = dn[3 * e + 2];
-            const float tol = CLS_EPS * (fabsf(nx) + fabsf(ny) + fabsf(nz));
-            int nin = 0, nout = 0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float d = fmaf(nx, sv[3 * i], fmaf(ny, sv[3 * i + 1], nz * sv[3 * i + 2]));
-                nin += d > tol; nout += d < -tol;
-            }
-            if (tol == 0.f) nin = 4;                   // zero-length edge (pole corner): n = 0 exactly, never cuts
-            empty |= nout == 4;
-            unsure |= nin + nout < 4;
-            if (nin < 4) cut |= 1u << e;
-        }
-        if (!empty && cut) {                           // reverse test: the destination corners against the source edges
-            float sn[12], dv[12];
-            load12(shd_s + (size_t)pr.x * 6 + 3, sn);
-            load12(shd_d + (size_t)pr.y * 6, dv);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float nx = sn[3 * j], ny = sn[3 * j + 1], nz = sn[3 * j + 2];
-                const float tol = CLS_EPS * (fabsf(nx) + fabsf(ny) + fabsf(nz));
-                int nout = 0;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) nout += fmaf(nx, dv[3 * e], fmaf(ny, dv[3 * e + 1], nz * dv[3 * e + 2])) < -tol;
-                empty |= nout == 4;
-            }
-        }
-        if (empty) state = -1;
-        else if (unsure) state = quad_prepass<3>(gs, pr.x, gd, pr.y);      // rare: the FP64 pre-pass decides
-        else state = (int)cut;
-        double area = 0.0;
-        if (state == 0 && unit_src_areas) { area = unit_src_areas[pr.x]; state = -1; }
-        if (state < 0) {
-            if (!(area > thresh) || !(area > 0.0)) area = 0.0;
-            area_out[idx] = area;
-            nonzero = area != 0.0;
-        }
-    }
-    // survivors decided here -> tile counter (a warp's 32 pairs lie in one tile)
-    const unsigned nzm = __ballot_sync(CRG_FULL, nonzero);
-    if (lane == 0 && nzm) atomicAdd(&tile_count[idx / CLIP_TILE], (uint32_t)__popc(nzm));
-    // jobs: single-cut from the front, multi-cut from the back
-    const bool job = idx < npairs && state >= 0;
-    const bool one = job && __popc((unsigned)state) <= 1;
-    const unsigned m1 = __ballot_sync(CRG_FULL, one), m2 = __ballot_sync(CRG_FULL, job && !one);
-    const unsigned lt = (1u << lane) - 1u;
-    // one global atomic per class per BLOCK (a global atomic per warp -- 840 K on two addresses for config 5 --
-    // serialised at the L2 and took 0.7 ms)
-    uint32_t b1 = 0, b2 = 0;
-    if (lane == 0) {
-        if (m1) b1 = atomicAdd(&s_cnt[0], (uint32_t)__popc(m1));
-        if (m2) b2 = atomicAdd(&s_cnt[1], (uint32_t)__popc(m2));
-    }
-    __syncthreads();
-    if (threadIdx.x < 2 && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&job_count[threadIdx.x], s_cnt[threadIdx.x]);
-    __syncthreads();
-    b1 = s_base[0] + __shfl_sync(CRG_FULL, b1, 0); b2 = s_base[1] + __shfl_sync(CRG_FULL, b2, 0);
-    const uint32_t rec = (uint32_t)idx | ((uint32_t)max(state, 0) << CLS_IDX_BITS);
-    if (one) jobs[b1 + __popc(m1 & lt)] = rec;
-    else if (job) jobs[(size_t)npairs - 1 - (b2 + __popc(m2 & lt))] = rec;
-}
-
-template <int NT>
-__global__ void __launch_bounds__(NT) cut_jobs_kernel(CellsView gd, CellsView gs, const double *__restrict__ nrm64_d,
-                                                      const int2 *__restrict__ pairs, int64_t npairs, double thresh,
-                                                      const uint32_t *__restrict__ jobs, const uint32_t *__restrict__ job_count,
-                                                      double *__restrict__ area_out, uint32_t *__restrict__ tile_count) {
-    extern __shared__ double clip_smem[];
-    const uint32_t c1 = job_count[0], total = c1 + job_count[1];
-    const uint32_t W = gridDim.x * NT;
-    const uint32_t padded = (total + 31u) & ~31u;      // warp-uniform trip count
-    auto fetch = [&](uint32_t t) -> uint32_t {
-        return t < total ? __ldg(t < c1 ? jobs + t : jobs + ((size_t)npairs - 1 - (t - c1))) : 0xffffffffu;
-    };
-    uint32_t t = blockIdx.x * NT + threadIdx.x;
-    uint32_t rec = fetch(t);
-    int2 pr = make_int2(0, 0);
-    if (rec != 0xffffffffu) pr = __ldg(pairs + (rec & ((1u << CLS_IDX_BITS) - 1u)));
-#pragma unroll 1
-    for (; t < padded; t += W) {
-        // the next job and its pair are in flight while this one is clipped
-        const uint32_t rec_n = t + W < padded ? fetch(t + W) : 0xffffffffu;
-        int2 pr_n = make_int2(0, 0);
-        if (rec_n != 0xffffffffu) pr_n = __ldg(pairs + (rec_n & ((1u << CLS_IDX_BITS) - 1u)));
-        const bool have = rec != 0xffffffffu;
-        uint32_t tile = 0xffffffffu;
-        if (have) {
-            const uint32_t jdx = rec & ((1u << CLS_IDX_BITS) - 1u);
-            double area = quad_cut_area<3, NT, true>(gs, pr.x, gd, pr.y, rec >> CLS_IDX_BITS, clip_smem, nrm64_d);
-            if (!(area > thresh) || !(area > 0.0)) area = 0.0;     // `area > 0` (intersection_areas.jl:24); NaN drops too
-            area_out[jdx] = area;
-            if (area != 0.0) tile = jdx / CLIP_TILE;
-        }
-        __syncwarp();
-        const unsigned same = __match_any_sync(CRG_FULL, tile);    // neighbouring jobs mostly share a tile
-        if (tile != 0xffffffffu && (threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&tile_count[tile], (uint32_t)__popc(same));
-        rec = rec_n; pr = pr_n;
-    }
-}
-
 // Stable compaction of the surviving pairs of one tile: tile_off = exclusive scan of tile_count.
 __global__ void __launch_bounds__(256) compact_pairs_kernel(const int2 *__restrict__ pairs, const double *__restrict__ area,
                                                             int64_t npairs, const uint32_t *__restrict__ tile_off,
