@@ -33,7 +33,7 @@ EXPORTS = [
     "crg_export_csc", "crg_export_csr", "crg_candidates", "crg_normalize", "crg_maximum", "crg_scale", "crg_apply", "crg_apply_async",
     "crg_set_stream", "crg_synchronize", "crg_apply_bytes", "crg_last_error", "crg_device_count", "crg_version",
     "crg_fp64_peak", "crg_launch_count", "crg_build_grids", "crg_grid_ncells", "crg_grid_cells",
-    "crg_clip_pairs", "crg_set_areas",
+    "crg_clip_pairs", "crg_set_areas", "crg_grid_areas",
 ]
 
 
@@ -56,10 +56,10 @@ class Cells(C.Structure):
 
 class GridDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("flags", C.c_int32), ("cells", Cells), ("n1", C.c_int64), ("n2", C.c_int64),
-                ("p", C.c_double * 4), ("lat_deg", C.c_void_p)]
+                ("p", C.c_double * 4), ("lat_deg", C.c_void_p), ("cell_lo", C.c_int64), ("cell_hi", C.c_int64)]
 
 
-GRID_CELLS, GRID_LONLAT, GRID_HEALPIX, GRID_FULL_RING, GRID_CUBED_SPHERE = 0, 1, 2, 3, 4
+GRID_CELLS, GRID_LONLAT, GRID_HEALPIX, GRID_FULL_RING, GRID_CUBED_SPHERE, GRID_REDUCED_RING = 0, 1, 2, 3, 4, 5
 
 
 class BuildStats(C.Structure):
@@ -125,6 +125,7 @@ def lib():
     L.crg_build_grids.argtypes = [P(Options), P(GridDesc), P(GridDesc), P(vp)]
     L.crg_grid_ncells.argtypes = [P(GridDesc), P(i64)]
     L.crg_grid_cells.argtypes = [P(GridDesc), i32, vp]
+    L.crg_grid_areas.argtypes = [P(Options), P(GridDesc), vp]
     L.crg_build_from_coo.argtypes = [P(Options), i64, i64, i64, vp, vp, vp, vp, vp, P(vp)]
     L.crg_free.argtypes = [vp]
     L.crg_dims.argtypes = [vp, P(i64), P(i64), P(i64)]

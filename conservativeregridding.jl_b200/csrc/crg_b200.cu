@@ -1141,7 +1141,18 @@ static int export_csr_matrix(const crg_regridder *R, const Csr &M, int32_t base,
 }
 
 // ---- described grids ---------------------------------------------------------------------------
+static int grid_ncells_full(const crg_grid *g, int64_t *n);
+// cells the descriptor stands for: the whole grid, or its slice [cell_lo, cell_hi)
 static int grid_ncells(const crg_grid *g, int64_t *n) {
+    CRG_TRY(grid_ncells_full(g, n));
+    if (g->kind != CRG_GRID_CELLS && (g->cell_lo != 0 || g->cell_hi != 0)) {
+        if (g->cell_lo < 0 || g->cell_hi < g->cell_lo || g->cell_hi > *n)
+            return set_error(CRG_ERR_INVALID, "grid slice [%lld, %lld) outside [0, %lld)", (long long)g->cell_lo, (long long)g->cell_hi, (long long)*n);
+        *n = g->cell_hi - g->cell_lo;
+    }
+    return CRG_OK;
+}
+static int grid_ncells_full(const crg_grid *g, int64_t *n) {
     if (!g) return set_error(CRG_ERR_INVALID, "null grid");
     switch (g->kind) {
         case CRG_GRID_CELLS: *n = g->cells.ncells; return CRG_OK;
@@ -1156,6 +1167,13 @@ static int grid_ncells(const crg_grid *g, int64_t *n) {
         case CRG_GRID_CUBED_SPHERE:
             if (g->n1 < 1) return set_error(CRG_ERR_INVALID, "cubed sphere: n must be positive");
             *n = 6 * g->n1 * g->n1; return CRG_OK;
+        case CRG_GRID_REDUCED_RING: {
+            const int64_t a = (int64_t)g->p[1], b = (int64_t)g->p[2], nh = g->n2 / 2;
+            if (g->n2 < 2 || (g->n2 & 1) || a < 1 || b < 0 || (double)a != g->p[1] || (double)b != g->p[2])
+                return set_error(CRG_ERR_INVALID, "reduced ring grid: n2 (rings) must be even and >= 2, p[1] >= 1 and p[2] >= 0 integers");
+            if (!g->lat_deg) return set_error(CRG_ERR_INVALID, "reduced ring grid: null lat_deg");
+            *n = 2 * (a * nh + b * (nh * (nh + 1) / 2)); return CRG_OK;
+        }
         default: return set_error(CRG_ERR_INVALID, "unknown grid kind %d", g->kind);
     }
 }
@@ -1164,16 +1182,18 @@ static int grid_ncells(const crg_grid *g, int64_t *n) {
 static int generate_grid(const crg_grid *g, int64_t n, double *verts, cudaStream_t st) {
     if (n == 0) return CRG_OK;
     const int nblk = ceil_div(n, 256);
+    const int64_t c0 = g->cell_lo, c1 = g->cell_lo + n;       // (whole grid: cell_lo = 0, n = all)
     switch (g->kind) {
         case CRG_GRID_LONLAT:
-            gen_lonlat_kernel<<<nblk, 256, 0, st>>>(g->n1, g->n2, g->p[0], g->p[1], g->p[2], g->p[3], verts);
+            gen_lonlat_kernel<<<nblk, 256, 0, st>>>(g->n1, g->n2, g->p[0], g->p[1], g->p[2], g->p[3], c0, c1, verts);
             break;
         case CRG_GRID_HEALPIX:
-            gen_healpix_kernel<<<nblk, 256, 0, st>>>(g->n1, g->flags & 1, verts);
+            gen_healpix_kernel<<<nblk, 256, 0, st>>>(g->n1, g->flags & 1, c0, c1, verts);
             break;
         case CRG_GRID_CUBED_SPHERE:
-            gen_cubed_sphere_kernel<<<nblk, 256, 0, st>>>(g->n1, verts);
+            gen_cubed_sphere_kernel<<<nblk, 256, 0, st>>>(g->n1, c0, c1, verts);
             break;
+        case CRG_GRID_REDUCED_RING:
         case CRG_GRID_FULL_RING: {
             const double *lat = g->lat_deg;
             DevBuf<double> dlat;
@@ -1182,12 +1202,36 @@ static int generate_grid(const crg_grid *g, int64_t n, double *verts, cudaStream
                 CRG_CUDA(cudaMemcpyAsync(dlat.p, lat, sizeof(double) * (size_t)g->n2, cudaMemcpyHostToDevice, st));
                 lat = dlat.p;
             }
-            gen_full_ring_kernel<<<nblk, 256, 0, st>>>(g->n1, g->n2, g->p[0], lat, verts);
+            if (g->kind == CRG_GRID_FULL_RING) gen_full_ring_kernel<<<nblk, 256, 0, st>>>(g->n1, g->n2, g->p[0], lat, c0, c1, verts);
+            else gen_reduced_ring_kernel<<<nblk, 256, 0, st>>>(g->n2, (int64_t)g->p[1], (int64_t)g->p[2], g->p[0], lat, c0, c1, verts);
             break;
         }
         default: return set_error(CRG_ERR_INVALID, "grid kind %d cannot be generated", g->kind);
     }
     CRG_LAUNCH_CHECK();
+    return CRG_OK;
+}
+
+template <int DIM>
+static int grid_areas_impl(const crg_options *opts, const crg_cells *c, double *areas, cudaStream_t st) {
+    DevCells g;
+    CRG_TRY(stage_cells(c, DIM, st, &g, "grid"));
+    const int64_t n = c->ncells;
+    DevBuf<double> a;
+    DevBuf<unsigned int> nflip;
+    DevBuf<BPStats> dstats;
+    CRG_TRY(a.alloc_tmp((size_t)n, st));
+    CRG_TRY(g.flip.alloc_tmp((size_t)n, st));
+    CRG_TRY(g.diam.alloc_tmp((size_t)n, st));
+    CRG_TRY(nflip.alloc_tmp(4, st));
+    CRG_TRY(dstats.alloc_tmp(1, st));
+    CRG_CUDA(cudaMemsetAsync(nflip.p, 0, 4 * sizeof(unsigned int), st));
+    CRG_CUDA(cudaMemsetAsync(dstats.p, 0, sizeof(BPStats), st));
+    const double r2 = DIM == 3 ? opts->radius * opts->radius : 1.0;
+    bp_bounds_kernel<DIM><<<ceil_div(n, 256), 256, 0, st>>>(g.view, g.diam.p, dstats.p, 1e30f, r2, a.p, g.flip.p, nflip.p);
+    CRG_LAUNCH_CHECK();
+    CRG_CUDA(cudaMemcpyAsync(areas, a.p, sizeof(double) * (size_t)n, cudaMemcpyDefault, st));
+    CRG_CUDA(cudaStreamSynchronize(st));
     return CRG_OK;
 }
 
@@ -1282,6 +1326,37 @@ int crg_grid_cells(const crg_grid *g, int32_t device, double *verts) {
     }
     CRG_CUDA(cudaStreamSynchronize(st));
     return CRG_OK;
+}
+
+int crg_grid_areas(const crg_options *opts, const crg_grid *g, double *areas) {
+    if (!opts || !g) return set_error(CRG_ERR_INVALID, "crg_grid_areas: null argument");
+    int64_t n = 0;
+    CRG_TRY(grid_ncells(g, &n));
+    if (n > 0 && !areas) return set_error(CRG_ERR_INVALID, "crg_grid_areas: null areas");
+    if (g->kind == CRG_GRID_CELLS) CRG_TRY(validate_cells(&g->cells, "grid"));
+    else if (opts->manifold != CRG_SPHERICAL) return set_error(CRG_ERR_INVALID, "crg_grid_areas: described grids live on the sphere");
+    if (!(opts->radius > 0.0)) return set_error(CRG_ERR_INVALID, "crg_grid_areas: radius must be positive");
+    CRG_TRY(check_device_available());
+    if (n == 0) return CRG_OK;
+    DeviceGuard guard;
+    CRG_TRY(guard.set(opts->device));
+    int dev = 0;
+    CRG_CUDA(cudaGetDevice(&dev));
+    cudaStream_t st = (cudaStream_t)opts->stream;
+    if (!st) CRG_TRY(device_stream(dev, &st));
+    ArenaScope arena;
+    int rc = arena.begin(dev, st);
+    DevBuf<double> verts;
+    crg_cells c = g->cells;
+    if (rc == CRG_OK && g->kind != CRG_GRID_CELLS) {
+        rc = verts.alloc_tmp((size_t)n * 12, st);
+        if (rc == CRG_OK) rc = generate_grid(g, n, verts.p, st);
+        c.verts = verts.p; c.offsets = nullptr; c.ncells = n; c.nv = 4; c.reserved = 0;
+    }
+    if (rc == CRG_OK) rc = (g->kind != CRG_GRID_CELLS || opts->manifold == CRG_SPHERICAL) ? grid_areas_impl<3>(opts, &c, areas, st)
+                                                                                         : grid_areas_impl<2>(opts, &c, areas, st);
+    if (rc != CRG_OK) { cudaStreamSynchronize(st); cudaGetLastError(); }
+    return rc;
 }
 
 int crg_build_grids(const crg_options *opts, const crg_grid *dst, const crg_grid *src, crg_regridder **out) {

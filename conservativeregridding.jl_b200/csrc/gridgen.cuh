@@ -37,9 +37,9 @@ __device__ __forceinline__ void geo_to_xyz(double slon, double clon, double slat
 
 // ---- regular lon-lat grid: cell (i, j), i (longitude) fastest, ring SW, SE, NE, NW -----------------
 __global__ void __launch_bounds__(256) gen_lonlat_kernel(int64_t nlon, int64_t nlat, double lon0, double lon1, double lat0,
-                                                         double lat1, double *__restrict__ verts) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nlon * nlat) return;
+                                                         double lat1, int64_t c0, int64_t c1, double *__restrict__ verts) {
+    const int64_t c = c0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c1) return;
     const int64_t i = c % nlon, j = c / nlon;
     const double lw = lon0 + (lon1 - lon0) * ((double)i / (double)nlon);
     const double le = lon0 + (lon1 - lon0) * ((double)(i + 1) / (double)nlon);
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) gen_lonlat_kernel(int64_t nlon, int64_t n
     double sw, cw, se, ce, ss, cs, sn, cn;
     sincosd_dev(lw, &sw, &cw); sincosd_dev(le, &se, &ce);
     sincosd_dev(ls, &ss, &cs); sincosd_dev(ln, &sn, &cn);
-    double *o = verts + c * 12;
+    double *o = verts + (c - c0) * 12;
     geo_to_xyz(sw, cw, ss, cs, o);
     geo_to_xyz(se, ce, ss, cs, o + 3);
     geo_to_xyz(se, ce, sn, cn, o + 6);
@@ -57,9 +57,10 @@ __global__ void __launch_bounds__(256) gen_lonlat_kernel(int64_t nlon, int64_t n
 
 // ---- RingGrids full grid: ring-major north -> south, pole-pinned latitude edges ---------------------------
 __global__ void __launch_bounds__(256) gen_full_ring_kernel(int64_t nlon, int64_t nlat, double lon_first,
-                                                            const double *__restrict__ latd, double *__restrict__ verts) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nlon * nlat) return;
+                                                            const double *__restrict__ latd, int64_t c0, int64_t c1,
+                                                            double *__restrict__ verts) {
+    const int64_t c = c0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c1) return;
     const int64_t i = c % nlon, r = c / nlon;
     const double top = r == 0 ? 90.0 : 0.5 * (latd[r - 1] + latd[r]);
     const double bot = r == nlat - 1 ? -90.0 : 0.5 * (latd[r] + latd[r + 1]);
@@ -69,7 +70,48 @@ __global__ void __launch_bounds__(256) gen_full_ring_kernel(int64_t nlon, int64_
     double sw, cw, se, ce, ss, cs, sn, cn;
     sincosd_dev(lw, &sw, &cw); sincosd_dev(le, &se, &ce);
     sincosd_dev(bot, &ss, &cs); sincosd_dev(top, &sn, &cn);
-    double *o = verts + c * 12;
+    double *o = verts + (c - c0) * 12;
+    geo_to_xyz(sw, cw, ss, cs, o);
+    geo_to_xyz(se, ce, ss, cs, o + 3);
+    geo_to_xyz(se, ce, sn, cn, o + 6);
+    geo_to_xyz(sw, cw, sn, cn, o + 9);
+}
+
+// ---- RingGrids reduced grid (octahedral Gaussian O<n>): ring of rank j from either pole has a + b j points --------
+// The reference has no cells for reduced grids (ext/ConservativeRegriddingRingGridsExt.jl:18-20 errors; upstream
+// issue #89): these generalise the full-grid rule -- latitude band between pole-pinned mid-latitudes x longitude
+// interval centred on the point -- exactly like grids.py::octahedral_gaussian_grid (BASELINE config 4).
+__device__ __forceinline__ int64_t reduced_ring_offset(int64_t j, int64_t a, int64_t b) {   // cells in the first j rings
+    return a * j + b * (j * (j + 1) / 2);
+}
+__global__ void __launch_bounds__(256) gen_reduced_ring_kernel(int64_t nlat, int64_t a, int64_t b, double lon_first,
+                                                               const double *__restrict__ latd, int64_t c0, int64_t c1,
+                                                               double *__restrict__ verts) {
+    const int64_t c = c0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nh = nlat / 2, half = reduced_ring_offset(nh, a, b);
+    if (c >= c1) return;
+    const bool south = c >= half;
+    const int64_t cc = south ? 2 * half - 1 - c : c;                 // mirror: the same ring rank counted from the south pole
+    // largest rn with offset(rn) <= cc: root of (b/2) r^2 + (a + b/2) r - cc = 0, then fixed up
+    const double B = (double)a + 0.5 * (double)b;
+    int64_t rn = b > 0 ? (int64_t)((-B + sqrt(B * B + 2.0 * (double)b * (double)cc)) / (double)b) : cc / a;
+    if (rn < 0) rn = 0;
+    if (rn > nh - 1) rn = nh - 1;
+    while (rn > 0 && reduced_ring_offset(rn, a, b) > cc) --rn;
+    while (rn < nh - 1 && reduced_ring_offset(rn + 1, a, b) <= cc) ++rn;
+    const int64_t n = a + b * (rn + 1);                               // points in this ring (rank j = rn + 1)
+    const int64_t r = south ? nlat - 1 - rn : rn;                     // ring index north -> south
+    const int64_t start = south ? 2 * half - reduced_ring_offset(rn + 1, a, b) : reduced_ring_offset(rn, a, b);
+    const int64_t i = c - start;
+    const double top = r == 0 ? 90.0 : 0.5 * (latd[r - 1] + latd[r]);
+    const double bot = r == nlat - 1 ? -90.0 : 0.5 * (latd[r] + latd[r + 1]);
+    const double dlon = 360.0 / (double)n;
+    const double lw = lon_first - dlon / 2 + (double)i * dlon;
+    const double le = lw + dlon;
+    double sw, cw, se, ce, ss, cs, sn, cn;
+    sincosd_dev(lw, &sw, &cw); sincosd_dev(le, &se, &ce);
+    sincosd_dev(bot, &ss, &cs); sincosd_dev(top, &sn, &cn);
+    double *o = verts + (c - c0) * 12;
     geo_to_xyz(sw, cw, ss, cs, o);
     geo_to_xyz(se, ce, ss, cs, o + 3);
     geo_to_xyz(se, ce, sn, cn, o + 6);
@@ -158,9 +200,10 @@ __device__ __forceinline__ void healpix_loc(double x, double y, int face, double
     o[0] = sth * cp; o[1] = sth * sp; o[2] = z;
 }
 // corners N, W, S, E (CCW from outside) = Healpix.boundariesRing(res, pix, 1)
-__global__ void __launch_bounds__(256) gen_healpix_kernel(int64_t nside, int nested, double *__restrict__ verts) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= 12 * nside * nside) return;
+__global__ void __launch_bounds__(256) gen_healpix_kernel(int64_t nside, int nested, int64_t c0, int64_t c1,
+                                                          double *__restrict__ verts) {
+    const int64_t c = c0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c1) return;
     int ix, iy, face;
     if (nested) {
         const int64_t npface = nside * nside;
@@ -173,7 +216,7 @@ __global__ void __launch_bounds__(256) gen_healpix_kernel(int64_t nside, int nes
     }
     const double x0 = (double)ix / (double)nside, x1 = (double)(ix + 1) / (double)nside;
     const double y0 = (double)iy / (double)nside, y1 = (double)(iy + 1) / (double)nside;
-    double *o = verts + c * 12;
+    double *o = verts + (c - c0) * 12;
     healpix_loc(x1, y1, face, o);       // N
     healpix_loc(x0, y1, face, o + 3);   // W
     healpix_loc(x0, y0, face, o + 6);   // S
@@ -187,13 +230,13 @@ __device__ __forceinline__ double cs_coord(int64_t i, int64_t n) {
     if (2 * i == n) return 0.0;
     return tan(-M_PI / 4 + (M_PI / 2) * ((double)i / (double)n));
 }
-__global__ void __launch_bounds__(256) gen_cubed_sphere_kernel(int64_t n, double *__restrict__ verts) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= 6 * n * n) return;
+__global__ void __launch_bounds__(256) gen_cubed_sphere_kernel(int64_t n, int64_t c0, int64_t c1, double *__restrict__ verts) {
+    const int64_t c = c0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c1) return;
     const int panel = (int)(c / (n * n));
     const int64_t k = c % (n * n), i = k % n, j = k / n;
     const int64_t ci[4] = {i, i + 1, i + 1, i}, cj[4] = {j, j, j + 1, j + 1};
-    double *o = verts + c * 12;
+    double *o = verts + (c - c0) * 12;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const double X = cs_coord(ci[q], n), Y = cs_coord(cj[q], n);

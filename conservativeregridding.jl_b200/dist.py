@@ -1,17 +1,23 @@
 """Destination-sharded multi-GPU regridder (one process per GPU, ``torch.distributed``).
 
 SURVEY.md section 8(e): destination cells are split into contiguous field-index blocks, one per
-rank; each rank builds the row block ``A_r`` of ``A`` for its destination cells against the
-*replicated* source grid -- ONE local build, no exchange during the build.
+rank; each rank builds the row block ``A_r`` of ``A`` for its destination cells against the HALO of
+the source grid that can reach its block -- ONE local build, no exchange during the build.
 
+* halo: the source cells whose latitude range meets the (inflated) latitude range of the block form a
+  contiguous index range for ring-major source grids (HEALPix ring, lon-lat, RingGrids full / octahedral);
+  described grids (:class:`GridSpec`) generate exactly that range on the device, so the per-rank cost of
+  the source side (cell bounds, binning, the rows of ``A_r^T``) shrinks with the number of ranks.  Other
+  orders (nested, cubed sphere) fall back to the replicated source + the build's own culling box.
 * forward ``regrid!``: the source field is broadcast (NCCL), every rank computes its block
-  ``y_r = (A_r x) ./ a_dst_r`` and the blocks are all-gathered;
+  ``y_r = (A_r x[halo]) ./ a_dst_r`` and the blocks are all-gathered;
 * ``transpose(R)``: ``A^T y = sum_r A_r^T y_r`` -- every rank applies the transpose of its own block
-  (the CSR(A_r^T) that the local assembly produces anyway) to its slice of the destination field
-  and the partial source vectors are summed with one all-reduce over NVLink; the division by the
-  (replicated, geometric) source areas follows the reduction.
-* ``R.dst_areas``: all-gather of the per-block areas; ``R.src_areas``: computed by every rank.
-* ``normalize=True``: every block is scaled by the all-reduced (max) ``maximum(A_r)``.
+  (the CSR(A_r^T) the local assembly produces anyway, division by the source areas fused: the areas are per
+  source cell, so dividing before the sum is the same) to its slice of the destination field; the partial
+  vectors only cover the rank's halo, they are ALL-GATHERED (no reduction collective) and overlap-added.
+* ``R.dst_areas``: all-gather of the per-block areas; ``R.src_areas``: every rank computes an equal share
+  (``crg_grid_areas``), all-gathered.
+* ``normalize=True``: every block is scaled by the all-reduced (max) ``maximum(A_r)`` (one scalar).
 
 The reference has no distributed path at all; the single-process semantics
 this reproduces are ``Regridder`` / ``regrid!`` / ``transpose`` (src/regridder/regridder.jl:125-163,
@@ -25,7 +31,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from .grids import Grid
+from .grids import Grid, GridSpec, ring_table
 
 
 def block_bounds(n: int, world: int) -> List[Tuple[int, int]]:
@@ -91,6 +97,69 @@ def candidate_weights(dst: Grid, src: Grid):
     return (ad.sqrt() + a_s ** 0.5) ** 2 / a_s
 
 
+def _z_range(block):
+    """(zmin, zmax) of the vertices of a destination block (Grid with numpy / torch vertices, or GridSpec)."""
+    if isinstance(block, GridSpec):
+        t = ring_table(block)
+        if t is None:
+            return None
+        start, zlo, zhi = t
+        lo, hi = (block.cell_lo, block.cell_hi) if (block.cell_lo or block.cell_hi) else (0, block.ncells_full)
+        if hi <= lo:
+            return None
+        r0 = int(np.searchsorted(start, lo, side="right")) - 1
+        r1 = int(np.searchsorted(start, hi - 1, side="right")) - 1
+        return float(min(zlo[r0:r1 + 1].min(), zhi[r0:r1 + 1].min())), float(max(zlo[r0:r1 + 1].max(), zhi[r0:r1 + 1].max()))
+    if block.manifold != 1 or block.ncells == 0:
+        return None
+    z = block.verts[..., 2]
+    return float(z.min()), float(z.max())
+
+
+def halo_range(block, src) -> Tuple[int, int]:
+    """Contiguous range [lo, hi) of source cells (indices of ``src`` as given) that can intersect the destination
+    ``block``: every source cell whose vertex latitude range, inflated by the bulge of great-circle edges over a
+    cell, meets the block's.  Tight for ring-major source orders; (0, n_src) when nothing is known."""
+    n_src = src.ncells
+    zr = _z_range(block)
+    if zr is None or n_src == 0:
+        return 0, n_src
+    # an edge of length d bulges by at most d^2 / 8 in z beyond its end points; d < 4 sqrt(4 pi / n) for the grids here
+    nd_full = block.ncells_full if isinstance(block, GridSpec) else None
+    d_dst = 4.0 * np.sqrt(4.0 * np.pi / max(nd_full or 0, 1)) if nd_full else None
+    if d_dst is None:                                     # explicit block: its own largest cell diameter
+        v = block.verts
+        if block.offsets is not None:
+            return 0, n_src
+        diff = v[:, :, None, :] - v[:, None, :, :] if v.shape[0] <= 4096 else v[::max(1, v.shape[0] // 4096)][:, :, None, :] - v[::max(1, v.shape[0] // 4096)][:, None, :, :]
+        d_dst = 2.0 * float((diff * diff).sum(-1).max()) ** 0.5
+    ns_full = src.ncells_full if isinstance(src, GridSpec) else src.ncells
+    d_src = 4.0 * np.sqrt(4.0 * np.pi / max(ns_full, 1))
+    margin = d_dst * d_dst + d_src * d_src + 1e-9
+    zmin, zmax = zr[0] - margin, zr[1] + margin
+    if isinstance(src, GridSpec):
+        t = ring_table(src)
+        if t is None:
+            return 0, n_src
+        start, zlo, zhi = t
+        hit = np.nonzero((zhi >= zmin) & (zlo <= zmax))[0]
+        if hit.size == 0:
+            return 0, 0
+        lo, hi = int(start[hit[0]]), int(start[hit[-1] + 1])
+        base = src.cell_lo if (src.cell_lo or src.cell_hi) else 0
+        top = src.cell_hi if (src.cell_lo or src.cell_hi) else src.ncells_full
+        lo, hi = max(lo, base), min(hi, top)
+        return (lo - base, max(hi, lo) - base)
+    if src.manifold != 1 or src.offsets is not None:
+        return 0, n_src
+    z = src.verts[..., 2]
+    hit = ((z.max(-1) >= zmin) & (z.min(-1) <= zmax)).nonzero()
+    hit = hit[0] if isinstance(hit, tuple) else hit.flatten()
+    if len(hit) == 0:
+        return 0, 0
+    return int(hit[0]), int(hit[-1]) + 1
+
+
 class _LocalB200:
     """Row-block operator backed by the CUDA engine (one ``crg_regridder`` handle)."""
 
@@ -128,10 +197,11 @@ class _LocalB200:
         from .regridder import regrid_
         regrid_(out, self.R, x, normalize=normalize, asynchronous=out.is_cuda)
 
-    def apply_T(self, out: torch.Tensor, y_block: torch.Tensor):
-        """out = A_r^T y_r (NOT divided: the division follows the cross-rank sum)"""
+    def apply_T(self, out: torch.Tensor, y_block: torch.Tensor, normalize: bool = False):
+        """out = A_r^T y_r, divided by the (halo) source areas when ``normalize`` (per source cell, so dividing
+        each rank's partial vector before the cross-rank sum equals dividing the sum)"""
         from .regridder import regrid_
-        regrid_(out, self.RT, y_block, normalize=False, asynchronous=out.is_cuda)
+        regrid_(out, self.RT, y_block, normalize=normalize, asynchronous=out.is_cuda)
 
 
 class ShardedRegridder:
@@ -142,17 +212,21 @@ class ShardedRegridder:
     numpy/scipy factory to exercise the sharding and the collectives under gloo.)
     ``balance``: False = equal cell counts per block; True = blocks of equal estimated candidate count
     (:func:`candidate_weights`); an array = per-destination-cell weights.  Collective when not False.
-    ``bounds``: explicit blocks (identical on every rank), e.g. ``dst_bounds`` of an earlier regridder."""
+    ``bounds``: explicit blocks (identical on every rank), e.g. ``dst_bounds`` of an earlier regridder.
+    ``halo``: build against the source halo of the block (:func:`halo_range`) instead of the replicated source.
+    ``areas_factory(grid) -> tensor``: geometric cell areas of a grid slice (default: ``crg_grid_areas``)."""
 
     def __init__(self, dst: Grid, src: Grid, group=None, local_factory: Optional[Callable] = None,
                  device: Optional[torch.device] = None, normalize: bool = False, balance=False,
-                 bounds: Optional[List[Tuple[int, int]]] = None):
+                 bounds: Optional[List[Tuple[int, int]]] = None, halo: bool = True,
+                 areas_factory: Optional[Callable] = None):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.n_dst, self.n_src = dst.ncells, src.ncells
         self.device = device if device is not None else torch.device("cpu")
         factory = local_factory or _LocalB200
+        self._areas_factory = areas_factory
         self.dst_bounds = block_bounds(self.n_dst, self.world)
         if bounds is not None:                            # e.g. the dst_bounds of an earlier balanced regridder
             assert len(bounds) == self.world and bounds[0][0] == 0 and bounds[-1][1] == self.n_dst
@@ -169,7 +243,12 @@ class ShardedRegridder:
             e = edges.cpu().tolist()
             self.dst_bounds = [(int(e[k]), int(e[k + 1])) for k in range(self.world)]
         lo, hi = self.dst_bounds[self.rank]
-        self.local = factory(dst.slice(lo, hi), src)
+        block = dst.slice(lo, hi)
+        self.src = src
+        self.src_range = halo_range(block, src) if (halo and self.world > 1) else (0, self.n_src)
+        self.local = factory(block, src.slice(*self.src_range) if self.src_range != (0, self.n_src) else src)
+        self._ranges = None           # every rank's halo range (collective, on first transpose)
+        self._scale = None
         if normalize:
             # normalize!(R) (regridder.jl:54-62): A, dst_areas, src_areas ./= maximum(A); the maximum of a
             # row-sharded A is the max over the blocks' maxima -- one scalar all-reduce.
@@ -178,6 +257,7 @@ class ShardedRegridder:
                 dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self.group)
             if float(m.item()) > 0.0:
                 self.local.scale(float(m.item()))
+                self._scale = float(m.item())
         self._dst_areas = None
         self._src_areas = None
         self._nnz = None
@@ -195,9 +275,42 @@ class ShardedRegridder:
 
     @property
     def src_areas(self) -> torch.Tensor:
+        """Geometric areas of ALL source cells (collective on first access): an equal share per rank, all-gathered."""
         if self._src_areas is None:
-            self._src_areas = self.local.src_areas(self.device).to(self.device)
+            if self.src_range == (0, self.n_src) and self.world == 1:
+                self._src_areas = self.local.src_areas(self.device).to(self.device)
+            else:
+                shares = block_bounds(self.n_src, self.world)
+                lo, hi = shares[self.rank]
+                mine = self._cell_areas(self.src.slice(lo, hi))
+                self._src_areas = self._all_gather_blocks(mine, shares)
+                if self._scale is not None:
+                    self._src_areas = self._src_areas / self._scale
         return self._src_areas
+
+    def _cell_areas(self, grid) -> torch.Tensor:
+        if self._areas_factory is not None:
+            return torch.as_tensor(self._areas_factory(grid), dtype=torch.float64).to(self.device)
+        from .regridder import areas
+        out = torch.empty(grid.ncells, dtype=torch.float64, device=self.device)
+        if out.is_cuda:
+            from .regridder import torch_stream_ptr
+            areas(grid, out=out, device=self.device.index, stream=torch_stream_ptr(self.device))
+            return out
+        return torch.from_numpy(areas(grid))
+
+    def halo_ranges(self) -> List[Tuple[int, int]]:
+        """Every rank's source halo range (collective on first call)."""
+        if self._ranges is None:
+            t = torch.tensor(list(self.src_range), dtype=torch.int64, device=self.device)
+            if self.world > 1:
+                allr = torch.empty(2 * self.world, dtype=torch.int64, device=self.device)
+                dist.all_gather_into_tensor(allr, t, group=self.group)
+                v = allr.cpu().tolist()
+            else:
+                v = t.cpu().tolist()
+            self._ranges = [(int(v[2 * k]), int(v[2 * k + 1])) for k in range(self.world)]
+        return self._ranges
 
     @property
     def nnz(self) -> int:
@@ -246,20 +359,38 @@ class ShardedRegridder:
         transpose: ``field`` is the destination field -- full length on every rank, or this rank's
         block -- and the result is the full source-grid field on every rank (all-reduce)."""
         lo, hi = self.dst_bounds[self.rank]
+        s_lo, s_hi = self.src_range
         if not transpose:
             x = self._broadcast(field, self.n_src, trailing) if broadcast else field
             out = torch.zeros((hi - lo,) + tuple(x.shape[1:]), dtype=torch.float64, device=x.device)
-            if hi > lo:
-                self.local.apply(out, x, normalize)
+            if hi > lo and s_hi > s_lo:
+                self.local.apply(out, x[s_lo:s_hi], normalize)           # the halo rows of x: a contiguous view
             return self._all_gather_blocks(out, self.dst_bounds) if gather else out
         y = field
         y_block = y if y.shape[0] == hi - lo and self.world > 1 else y[lo:hi]
-        part = torch.zeros((self.n_src,) + tuple(y.shape[1:]), dtype=torch.float64, device=y.device)
-        if hi > lo:
-            self.local.apply_T(part, y_block.contiguous())
-        if self.world > 1:
-            dist.all_reduce(part, group=self.group)
-        if normalize:
-            a = self.src_areas
-            part /= a if part.dim() == 1 else a[:, None]
-        return part
+        part = torch.zeros((s_hi - s_lo,) + tuple(y.shape[1:]), dtype=torch.float64, device=y.device)
+        if hi > lo and s_hi > s_lo:
+            self.local.apply_T(part, y_block.contiguous(), normalize)
+        if self.world == 1:
+            if (s_lo, s_hi) == (0, self.n_src):
+                return part
+            full = torch.zeros((self.n_src,) + tuple(y.shape[1:]), dtype=torch.float64, device=y.device)
+            full[s_lo:s_hi] = part
+            return full
+        if not gather:
+            return part                                                 # covers source cells self.src_range
+        # all-gather of the halo partials + overlap-add: no reduction collective (the halos of neighbouring
+        # blocks share a few rings, everything else is written once)
+        ranges = self.halo_ranges()
+        width = max(b - a for a, b in ranges)
+        pad = part
+        if part.shape[0] != width:
+            pad = torch.zeros((width,) + tuple(part.shape[1:]), dtype=torch.float64, device=part.device)
+            pad[: part.shape[0]] = part
+        allp = torch.empty((self.world * width,) + tuple(part.shape[1:]), dtype=torch.float64, device=part.device)
+        dist.all_gather_into_tensor(allp, pad.contiguous(), group=self.group)
+        full = torch.zeros((self.n_src,) + tuple(y.shape[1:]), dtype=torch.float64, device=y.device)
+        for k, (a, b) in enumerate(ranges):
+            if b > a:
+                full[a:b] += allp[k * width: k * width + (b - a)]
+        return full

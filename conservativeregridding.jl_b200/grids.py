@@ -84,7 +84,7 @@ class Grid:
 class GridSpec:
     """A structured grid described by a few numbers; its cell vertices are generated ON THE DEVICE
     inside ``crg_build_grids`` (csrc/gridgen.cuh), so no vertex soup is built or uploaded by the
-    host.  ``kind``: "lonlat" | "healpix" | "full_ring" | "cubed_sphere" (include/crg_b200.h).
+    host.  ``kind``: "lonlat" | "healpix" | "full_ring" | "cubed_sphere" | "reduced_ring" (include/crg_b200.h).
     ``materialize()`` gives the equivalent host :class:`Grid` (same conventions, same order)."""
 
     kind: str
@@ -96,16 +96,42 @@ class GridSpec:
     radius: float = 1.0
     name: str = ""
     manifold: int = 1
+    cell_lo: int = 0          # a slice [cell_lo, cell_hi) of the field-linear order (0, 0 = the whole grid)
+    cell_hi: int = 0
 
     @property
     def ncells(self) -> int:
+        if self.cell_lo or self.cell_hi:
+            return self.cell_hi - self.cell_lo
+        return self.ncells_full
+
+    def slice(self, lo: int, hi: int) -> "GridSpec":
+        """Cells [lo, hi) of this (possibly already sliced) grid -- a destination block or a source halo of a
+        sharded build; still generated on the device."""
+        import dataclasses
+        n = self.ncells
+        if not (0 <= lo <= hi <= n):
+            raise IndexError(f"slice [{lo}, {hi}) outside [0, {n})")
+        base = self.cell_lo
+        if lo == 0 and hi == n and not (self.cell_lo or self.cell_hi):
+            return self
+        return dataclasses.replace(self, cell_lo=base + lo, cell_hi=base + hi, name=f"{self.name}[{lo}:{hi}]")
+
+    @property
+    def ncells_full(self) -> int:
         if self.kind == "healpix":
             return 12 * self.n1 * self.n1
         if self.kind == "cubed_sphere":
             return 6 * self.n1 * self.n1
+        if self.kind == "reduced_ring":
+            a, b, nh = int(self.p[1]), int(self.p[2]), self.n2 // 2
+            return 2 * (a * nh + b * (nh * (nh + 1) // 2))
         return self.n1 * self.n2
 
     def materialize(self) -> "Grid":
+        if self.cell_lo or self.cell_hi:
+            import dataclasses
+            return dataclasses.replace(self, cell_lo=0, cell_hi=0).materialize().slice(self.cell_lo, self.cell_hi)
         if self.kind == "lonlat":
             return lonlat_grid(self.n1, self.n2, *self.p, radius=self.radius)
         if self.kind == "healpix":
@@ -114,7 +140,42 @@ class GridSpec:
             return full_ring_grid(self.lat_deg, self.n1, self.p[0], self.radius, self.name or "fullring")
         if self.kind == "cubed_sphere":
             return cubed_sphere_grid(self.n1, radius=self.radius)
+        if self.kind == "reduced_ring":
+            return octahedral_gaussian_grid(self.n2 // 2, radius=self.radius)
         raise ValueError(self.kind)
+
+
+def ring_table(g):
+    """For DESCRIBED grids whose field-linear order is ring-major (cells of one latitude band are contiguous): per
+    ring the first cell index (of the whole grid) and the z = sin(lat) range of its cells' VERTICES --
+    ``(start[nr + 1], zlo[nr], zhi[nr])`` in ring order -- else None.  A destination block's z-range then selects the contiguous source cell range that can
+    reach it (the halo of a sharded build, dist.py)."""
+    if not isinstance(g, GridSpec):
+        return None
+    kind, n1, n2, p, flags, latd = g.kind, g.n1, g.n2, g.p, g.flags, g.lat_deg
+    sind = lambda d: np.sin(np.radians(np.asarray(d, dtype=np.float64)))  # noqa: E731
+    if kind == "lonlat":
+        e = sind(p[2] + (p[3] - p[2]) * np.arange(n2 + 1) / n2)           # south -> north
+        return np.arange(n2 + 1, dtype=np.int64) * n1, e[:-1], e[1:]
+    if kind in ("full_ring", "reduced_ring"):
+        e = sind(_pole_pinned_lat_edges(np.asarray(latd, dtype=np.float64)))    # north -> south
+        if kind == "full_ring":
+            start = np.arange(n2 + 1, dtype=np.int64) * n1
+        else:
+            a, b, nh = int(p[1]), int(p[2]), n2 // 2
+            j = np.concatenate([np.arange(1, nh + 1), np.arange(nh, 0, -1)])
+            start = np.concatenate([[0], np.cumsum(a + b * j)]).astype(np.int64)
+        return start, e[1:], e[:-1]
+    if kind == "healpix" and not (flags & 1):
+        ns = n1
+        i = np.arange(0, 4 * ns + 1, dtype=np.float64)                   # ring index 0 (north pole) .. 4 nside (south pole)
+        zc = np.where(i <= ns, 1.0 - i * i / (3.0 * ns * ns),
+                      np.where(i <= 3 * ns, 4.0 / 3.0 - 2.0 * i / (3.0 * ns), -1.0 + (4 * ns - i) ** 2 / (3.0 * ns * ns)))
+        r = np.arange(1, 4 * ns)                                          # rings 1 .. 4 nside - 1, north -> south
+        npix = np.where(r < ns, 4 * r, np.where(r <= 3 * ns, 4 * ns, 4 * (4 * ns - r)))
+        start = np.concatenate([[0], np.cumsum(npix)]).astype(np.int64)
+        return start, zc[r + 1], zc[r - 1]                                # a pixel's N / S corners sit on the neighbouring rings
+    return None
 
 
 def lonlat_spec(nlon, nlat, lon0=0.0, lon1=360.0, lat0=-90.0, lat1=90.0, radius=1.0) -> GridSpec:
@@ -137,6 +198,13 @@ def full_clenshaw_spec(nlat_half, radius=1.0) -> GridSpec:
     latd = 90.0 - 90.0 * (np.arange(1, nlat + 1) / nlat_half)
     return GridSpec("full_ring", 4 * nlat_half, nlat, (0.0, 0.0, 0.0, 0.0), 0, np.ascontiguousarray(latd), radius,
                     f"FullClenshaw{nlat_half}")
+
+
+def octahedral_gaussian_spec(nlat_half, radius=1.0) -> GridSpec:
+    """O<nlat_half> (SpeedyWeather's default grid, BASELINE config 4): 2*nlat_half Gaussian rings, 16 + 4j points in
+    the ring of rank j from either pole (= :func:`octahedral_gaussian_grid`, generated on the device)."""
+    return GridSpec("reduced_ring", 0, 2 * nlat_half, (0.0, 16.0, 4.0, 0.0), 0,
+                    np.ascontiguousarray(gaussian_latitudes(2 * nlat_half)), radius, f"O{nlat_half}")
 
 
 def cubed_sphere_spec(n, radius=1.0) -> GridSpec:

@@ -72,7 +72,7 @@ def as_grid(obj, manifold: Optional[int] = None, radius: float = 1.0) -> Grid:
 
 
 _KINDS = {"lonlat": _lib.GRID_LONLAT, "healpix": _lib.GRID_HEALPIX, "full_ring": _lib.GRID_FULL_RING,
-          "cubed_sphere": _lib.GRID_CUBED_SPHERE}
+          "cubed_sphere": _lib.GRID_CUBED_SPHERE, "reduced_ring": _lib.GRID_REDUCED_RING}
 
 
 def _grid_struct(g, keep: list) -> _lib.GridDesc:
@@ -84,6 +84,7 @@ def _grid_struct(g, keep: list) -> _lib.GridDesc:
         d.n1, d.n2 = g.n1, g.n2
         for i in range(4):
             d.p[i] = g.p[i]
+        d.cell_lo, d.cell_hi = g.cell_lo, g.cell_hi
         if g.lat_deg is not None:
             lat = np.ascontiguousarray(g.lat_deg, dtype=np.float64)
             keep.append(lat)
@@ -700,19 +701,18 @@ def regrid(R: RegridderB200, src_field, **kw):
     return regrid_(dst, R, src_field, **kw)
 
 
-def areas(grid, manifold: Optional[int] = None) -> np.ndarray:
-    """``areas(manifold, x, tree)`` for one grid (regridder.jl:165-178), computed on the device."""
+def areas(grid, manifold: Optional[int] = None, out=None, device: Optional[int] = None, stream: Optional[int] = None):
+    """``areas(manifold, x, tree)`` = ``[GO.area(manifold, cell) for cell in getcell(tree)]`` for one grid
+    (regridder.jl:165-178), computed on the device (``crg_grid_areas``).  ``out``: numpy array or CUDA tensor to
+    fill (default: a new numpy vector)."""
     g = as_grid(grid, manifold)
-    if isinstance(g, GridSpec):                       # described grid: any one-cell partner will do
-        one = np.array([[[1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]]])
-        tiny = Grid(one, SPHERICAL, None, g.radius)
-    else:
-        first = g.verts[:1] if g.offsets is None else g.cell(0)[None]
-        if _is_torch(first):
-            first = first.cpu().numpy()
-        tiny = Grid(np.array(first, dtype=np.float64), g.manifold, None, g.radius)
-    R = Regridder(g, tiny, build_transpose=False)
-    return R.dst_areas
+    keep = []
+    d = _grid_struct(g, keep)
+    if out is None:
+        out = np.empty(g.ncells, dtype=np.float64)
+    o = _make_options(g.manifold, False, g.radius, device, 0.0, False, False, stream)
+    _lib.check(_lib.lib().crg_grid_areas(C.byref(o), C.byref(d), C.c_void_p(_ptr(out))))
+    return out
 
 
 def clip_pairs(dst, src, src_idx, dst_idx, *, manifold: Optional[int] = None, radius: Optional[float] = None,

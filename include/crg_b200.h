@@ -95,12 +95,19 @@ typedef struct crg_cells {
  *                         n1 = nlon, n2 = nlat, p[0] = longitude of the first point, lat_deg = the nlat
  *                         ring latitudes in degrees, north -> south (host or device pointer)
  *   CRG_GRID_CUBED_SPHERE equiangular gnomonic cubed sphere, n1 = cells per panel edge; 6 panels,
- *                         panel-major (each panel is a CellBasedGrid, src/trees/grids.jl:57-85)      */
+ *                         panel-major (each panel is a CellBasedGrid, src/trees/grids.jl:57-85)
+ *   CRG_GRID_REDUCED_RING RingGrids reduced grid (octahedral Gaussian O<n>: SpeedyWeather's default); the reference
+ *                         has NO cells for it (ext/ConservativeRegriddingRingGridsExt.jl:18-20 errors): the full-grid
+ *                         rule generalised -- band between pole-pinned mid-latitudes x longitude interval centred on
+ *                         the point.  n2 = number of rings (even), lat_deg = ring latitudes north -> south, the ring of
+ *                         rank j = 1, 2, .. from either pole has p[1] + p[2] * j points (octahedral: 16 + 4 j), p[0] =
+ *                         longitude of the first point of every ring; ring-major north -> south, longitude fastest */
 #define CRG_GRID_CELLS 0
 #define CRG_GRID_LONLAT 1
 #define CRG_GRID_HEALPIX 2
 #define CRG_GRID_FULL_RING 3
 #define CRG_GRID_CUBED_SPHERE 4
+#define CRG_GRID_REDUCED_RING 5
 
 typedef struct crg_grid {
     int32_t kind;
@@ -109,6 +116,8 @@ typedef struct crg_grid {
     int64_t n1, n2;
     double p[4];
     const double *lat_deg;
+    int64_t cell_lo, cell_hi; /* described grids: only the cells [cell_lo, cell_hi) of the field-linear order (a        */
+                              /* destination block or a source halo of a sharded build); 0, 0 = the whole grid       */
 } crg_grid;
 
 /* Counters and per-phase device times (CUDA events, milliseconds) of the last build. */
@@ -137,6 +146,11 @@ int crg_build_grids(const crg_options *opts, const crg_grid *dst, const crg_grid
  * generated on `device` -- what crg_build_grids feeds to the build (tests / export).             */
 int crg_grid_ncells(const crg_grid *g, int64_t *ncells);
 int crg_grid_cells(const crg_grid *g, int32_t device, double *verts);
+
+/* areas(manifold, x, tree) = [GO.area(manifold, cell) for cell in getcell(tree)] for ONE grid
+ * (src/regridder/regridder.jl:165-178): geometric cell areas * radius^2, ncells doubles (host or device).
+ * (A sharded regridder computes the areas of the replicated side in equal shares, one per rank.)               */
+int crg_grid_areas(const crg_options *opts, const crg_grid *g, double *areas);
 
 /* Assemble from explicit (dst_idx, src_idx, area) triples (0-based; duplicates are summed;
  * non-positive areas must already be dropped by the caller, intersection_areas.jl:24).

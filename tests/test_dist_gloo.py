@@ -18,6 +18,7 @@ class _OracleLocal:
 
     def __init__(self, rows_grid, cols_grid):
         from oracle import oracle
+        rows_grid, cols_grid = _explicit(rows_grid), _explicit(cols_grid)
         self.O = oracle.build_regridder(rows_grid, cols_grid)
         self.A = self.O.tocsc().tocsr()
         self.nnz = self.O.nnz
@@ -42,8 +43,20 @@ class _OracleLocal:
             y = y / (self.O.dst_areas if y.ndim == 1 else self.O.dst_areas[:, None])
         out.copy_(torch.from_numpy(np.asarray(y)))
 
-    def apply_T(self, out, y_block):
-        out.copy_(torch.from_numpy(np.asarray(self.A.T @ y_block.numpy())))
+    def apply_T(self, out, y_block, normalize=False):
+        x = self.A.T @ y_block.numpy()
+        if normalize:
+            x = x / (self.O.src_areas if x.ndim == 1 else self.O.src_areas[:, None])
+        out.copy_(torch.from_numpy(np.asarray(x)))
+
+
+def _explicit(g):
+    return g.materialize() if hasattr(g, "materialize") else g
+
+
+def _oracle_areas(g):
+    from oracle import oracle
+    return oracle.cell_areas(_explicit(g))
 
 
 def _worker(rank, world, port, q):
@@ -56,7 +69,7 @@ def _worker(rank, world, port, q):
         from crg_b200.dist import ShardedRegridder, block_bounds
         from oracle import oracle
         dst, src = grids.lonlat_grid(25, 13), grids.healpix_grid(4, "ring")      # 325 cells: uneven blocks
-        S = ShardedRegridder(dst, src, local_factory=_OracleLocal)
+        S = ShardedRegridder(dst, src, local_factory=_OracleLocal, areas_factory=_oracle_areas)
         full = oracle.build_regridder(dst, src)
         assert S.nnz == full.nnz and S.shape == (dst.ncells, src.ncells)
         assert np.allclose(S.dst_areas.numpy(), full.dst_areas, rtol=1e-15)
@@ -82,7 +95,7 @@ def _worker(rank, world, port, q):
         yl = S.regrid(torch.from_numpy(x0), broadcast=False, gather=False)
         assert yl.shape[0] == hi - lo and np.allclose(yl.numpy(), full.regrid(x0)[lo:hi], rtol=1e-13)
         # blocks balanced by estimated candidate count (rank 0 decides, bounds broadcast): same results
-        Sb = ShardedRegridder(dst, src, local_factory=_OracleLocal, balance=True)
+        Sb = ShardedRegridder(dst, src, local_factory=_OracleLocal, areas_factory=_oracle_areas, balance=True)
         assert Sb.dst_bounds[0][0] == 0 and Sb.dst_bounds[-1][1] == dst.ncells
         assert all(a[1] == b[0] for a, b in zip(Sb.dst_bounds[:-1], Sb.dst_bounds[1:]))
         if world == 3:                                         # (two blocks of a symmetric grid are balanced already)
@@ -93,13 +106,35 @@ def _worker(rank, world, port, q):
         xbb = Sb.regrid(yb, transpose=True)
         assert np.allclose(xbb.numpy(), xb.numpy(), rtol=1e-12)
         # normalize!(R): every block scaled by the global maximum(A) (one scalar all-reduce)
-        Sn = ShardedRegridder(dst, src, local_factory=_OracleLocal, normalize=True)
+        Sn = ShardedRegridder(dst, src, local_factory=_OracleLocal, areas_factory=_oracle_areas, normalize=True)
         m = full.tocsc().max()
         assert np.allclose(Sn.dst_areas.numpy(), full.dst_areas / m, rtol=1e-15)
         assert np.allclose(Sn.src_areas.numpy(), full.src_areas / m, rtol=1e-15)
         assert abs(max(Sn.local.maximum(), 0.0) - (full.tocsc()[lo:hi].max() / m)) < 1e-15
         yn = Sn.regrid(torch.from_numpy(x0), broadcast=False)
         assert np.allclose(yn.numpy(), full.regrid(x0), rtol=1e-13)          # the normalisation cancels in regrid!
+        # halo-sliced sources: described grids (ring tables) and explicit cells (per-cell latitude ranges); every rank
+        # builds against a strict subset of the source, the transpose is all-gather + overlap-add (no reduction)
+        dspec, sspec = grids.lonlat_spec(60, 30), grids.healpix_spec(16, "ring")
+        fullh = oracle.build_regridder(dspec.materialize(), sspec.materialize())
+        xh = np.random.default_rng(1).random(sspec.ncells)
+        for d_, s_ in ((dspec, sspec), (dspec.materialize(), sspec.materialize()), (dspec, sspec.materialize())):
+            Sh = ShardedRegridder(d_, s_, local_factory=_OracleLocal, areas_factory=_oracle_areas)
+            a, b = Sh.src_range
+            assert 0 <= a < b <= sspec.ncells and (b - a) < sspec.ncells, (a, b)
+            assert Sh.nnz == fullh.nnz
+            assert np.allclose(Sh.src_areas.numpy(), fullh.src_areas, rtol=1e-15)
+            yh = Sh.regrid(torch.from_numpy(xh), broadcast=False)
+            assert np.allclose(yh.numpy(), fullh.regrid(xh), rtol=1e-13)
+            xbh = Sh.regrid(yh, transpose=True)
+            assert np.allclose(xbh.numpy(), fullh.regrid(fullh.regrid(xh), transpose=True), rtol=1e-12)
+            part = Sh.regrid(yh, transpose=True, gather=False)
+            assert part.shape[0] == b - a
+        # the halo must contain every source cell that meets the block (else entries would be missing): nnz above;
+        # without halos the same results
+        Sn0 = ShardedRegridder(dspec, sspec, local_factory=_OracleLocal, areas_factory=_oracle_areas, halo=False)
+        assert Sn0.src_range == (0, sspec.ncells)
+        assert np.allclose(Sn0.regrid(torch.from_numpy(xh), broadcast=False).numpy(), fullh.regrid(xh), rtol=1e-13)
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback

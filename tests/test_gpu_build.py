@@ -274,6 +274,8 @@ SPECS = {
     "gaussian": lambda: grids.full_gaussian_spec(16),
     "clenshaw": lambda: grids.full_clenshaw_spec(12),
     "cubed_sphere": lambda: grids.cubed_sphere_spec(10),
+    "octahedral": lambda: grids.octahedral_gaussian_spec(24),
+    "octahedral_O320": lambda: grids.octahedral_gaussian_spec(320),       # BASELINE config 4
 }
 
 
@@ -297,7 +299,9 @@ def test_described_grids_build_the_same_regridder(gpu):
     from crg_b200.regridder import grid_cells
     pairs = [(grids.lonlat_spec(90, 45), grids.healpix_spec(16, "ring")),
              (grids.healpix_spec(8, "nested"), grids.lonlat_spec(48, 24)),
-             (grids.full_gaussian_spec(12), grids.cubed_sphere_spec(8))]
+             (grids.full_gaussian_spec(12), grids.cubed_sphere_spec(8)),
+             (grids.full_gaussian_spec(16), grids.octahedral_gaussian_spec(32)),
+             (grids.octahedral_gaussian_spec(12), grids.lonlat_spec(40, 20))]
     for ds, ss in pairs:
         R1 = Regridder(ds, ss)
         R2 = Regridder(ds.materialize(), ss.materialize())

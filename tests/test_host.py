@@ -126,3 +126,29 @@ def test_balanced_bounds_and_candidate_weights():
     cw = candidate_weights(dst, src).numpy().reshape(18, 36)
     assert cw[9, 0] > 1.5 * cw[0, 0]                                       # equatorial cells have more candidates
     assert candidate_weights(grids.polygons_grid([np.array([[0, 0], [1, 0], [0, 1.0]])]), src) is None
+
+
+def test_octahedral_spec_counts_and_materialises():
+    """The octahedral descriptor (BASELINE config 4; no reference cells exist, RingGridsExt.jl:18-20): O320 has
+    421 120 cells, ring of rank j has 16 + 4 j of them, and the host cells are what materialize() returns."""
+    sp = grids.octahedral_gaussian_spec(320)
+    assert sp.ncells == 421120 and sp.kind == "reduced_ring" and sp.n2 == 640
+    small = grids.octahedral_gaussian_spec(6)
+    g = small.materialize()
+    assert g.ncells == small.ncells == 2 * sum(16 + 4 * j for j in range(1, 7))
+    assert np.array_equal(g.verts, grids.octahedral_gaussian_grid(6).verts)
+
+
+def test_kernel_counters_match_the_shipped_sources():
+    """bench.py takes the clip kernel's FP64 work per pair and the DRAM traffic figures from
+    profiles/r02_kernel_counters.json (ncu captures of the shipped kernels); they are only valid for the sources
+    they were measured on.  Re-run scripts/final_profile.sh after touching geom.cuh / kernels.cuh / sell.cuh."""
+    import json
+    import bench
+    p = bench.COUNTERS_JSON
+    if not os.path.exists(p):
+        pytest.skip("no counters file yet")
+    d = json.load(open(p))
+    for name, e in d.items():
+        assert e["src_hash"] == bench.source_hash(e["src_files"]), f"{name}: kernel sources changed since the ncu capture"
+    assert 100 < d["clip"]["flops_per_pair"] < 2000
