@@ -116,10 +116,30 @@ def _z_range(block):
     return float(z.min()), float(z.max())
 
 
+_HALO_CACHE = {}
+
+
+def _spec_key(g: GridSpec):
+    return (g.kind, g.n1, g.n2, tuple(g.p), g.flags, g.cell_lo, g.cell_hi,
+            None if g.lat_deg is None else hash(np.asarray(g.lat_deg).tobytes()))
+
+
 def halo_range(block, src) -> Tuple[int, int]:
     """Contiguous range [lo, hi) of source cells (indices of ``src`` as given) that can intersect the destination
     ``block``: every source cell whose vertex latitude range, inflated by the bulge of great-circle edges over a
-    cell, meets the block's.  Tight for ring-major source orders; (0, n_src) when nothing is known."""
+    cell, meets the block's.  Tight for ring-major source orders; (0, n_src) when nothing is known.
+    (For two described grids the answer is a property of the descriptors and is remembered.)"""
+    if isinstance(block, GridSpec) and isinstance(src, GridSpec):
+        key = (_spec_key(block), _spec_key(src))
+        if key not in _HALO_CACHE:
+            if len(_HALO_CACHE) > 4096:
+                _HALO_CACHE.clear()
+            _HALO_CACHE[key] = _halo_range(block, src)
+        return _HALO_CACHE[key]
+    return _halo_range(block, src)
+
+
+def _halo_range(block, src) -> Tuple[int, int]:
     n_src = src.ncells
     zr = _z_range(block)
     if zr is None or n_src == 0:
@@ -362,15 +382,19 @@ class ShardedRegridder:
         s_lo, s_hi = self.src_range
         if not transpose:
             x = self._broadcast(field, self.n_src, trailing) if broadcast else field
-            out = torch.zeros((hi - lo,) + tuple(x.shape[1:]), dtype=torch.float64, device=x.device)
             if hi > lo and s_hi > s_lo:
+                out = torch.empty((hi - lo,) + tuple(x.shape[1:]), dtype=torch.float64, device=x.device)
                 self.local.apply(out, x[s_lo:s_hi], normalize)           # the halo rows of x: a contiguous view
+            else:
+                out = torch.zeros((hi - lo,) + tuple(x.shape[1:]), dtype=torch.float64, device=x.device)
             return self._all_gather_blocks(out, self.dst_bounds) if gather else out
         y = field
         y_block = y if y.shape[0] == hi - lo and self.world > 1 else y[lo:hi]
-        part = torch.zeros((s_hi - s_lo,) + tuple(y.shape[1:]), dtype=torch.float64, device=y.device)
         if hi > lo and s_hi > s_lo:
+            part = torch.empty((s_hi - s_lo,) + tuple(y.shape[1:]), dtype=torch.float64, device=y.device)
             self.local.apply_T(part, y_block.contiguous(), normalize)
+        else:
+            part = torch.zeros((s_hi - s_lo,) + tuple(y.shape[1:]), dtype=torch.float64, device=y.device)
         if self.world == 1:
             if (s_lo, s_hi) == (0, self.n_src):
                 return part
@@ -389,8 +413,31 @@ class ShardedRegridder:
             pad[: part.shape[0]] = part
         allp = torch.empty((self.world * width,) + tuple(part.shape[1:]), dtype=torch.float64, device=part.device)
         dist.all_gather_into_tensor(allp, pad.contiguous(), group=self.group)
-        full = torch.zeros((self.n_src,) + tuple(y.shape[1:]), dtype=torch.float64, device=y.device)
-        for k, (a, b) in enumerate(ranges):
-            if b > a:
-                full[a:b] += allp[k * width: k * width + (b - a)]
+        # ranges of ring-major halos are increasing with the rank: block k is COPIED where nothing was written yet and
+        # ADDED where it overlaps its predecessors; source cells no block reaches stay zero
+        full = torch.empty((self.n_src,) + tuple(y.shape[1:]), dtype=torch.float64, device=y.device)
+        done = 0                                         # cells [0, done) are written
+        order = sorted(range(self.world), key=lambda k: ranges[k])
+        monotone = all(ranges[order[i]][1] <= ranges[order[i + 1]][1] for i in range(self.world - 1))
+        if not monotone:
+            full.zero_()
+            for k, (a, b) in enumerate(ranges):
+                if b > a:
+                    full[a:b] += allp[k * width: k * width + (b - a)]
+            return full
+        for k in order:
+            a, b = ranges[k]
+            if b <= a:
+                continue
+            blk = allp[k * width: k * width + (b - a)]
+            if a > done:
+                full[done:a].zero_()
+            ov = max(min(done, b) - a, 0)                # [a, a + ov) already written: add
+            if ov > 0:
+                full[a:a + ov] += blk[:ov]
+            if b > a + ov:
+                full[a + ov:b] = blk[ov:]
+            done = max(done, b)
+        if done < self.n_src:
+            full[done:].zero_()
         return full
