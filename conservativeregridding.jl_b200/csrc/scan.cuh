@@ -1,8 +1,7 @@
 // scan.cuh -- device-wide exclusive prefix sum (hand-written; no CUB/Thrust).
 //
-// Three-kernel reduce / scan-of-sums / downsweep with 4096-element tiles, recursing on the
-// tile sums.  out has n+1 entries: out[i] = sum_{j<i} in[j], out[n] = total.  HBM-bound:
-// 2 reads + 1 write of the input per level.
+// out has n+1 entries: out[i] = sum_{j<i} in[j], out[n] = total.  Inputs of at most one 4096-element tile take
+// one block; longer ones the single-pass decoupled-look-back kernel below.  HBM-bound: one read + one write.
 #pragma once
 #include "common.cuh"
 
@@ -11,28 +10,6 @@ namespace crg {
 constexpr int SCAN_THREADS = 1024;
 constexpr int SCAN_ITEMS = 4;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
-
-template <typename Tin, typename Tout>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const Tin *__restrict__ in, int64_t n,
-                                                                   Tout *__restrict__ tile_sums) {
-    __shared__ Tout sm[33];
-    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
-    Tout s = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        int64_t i = base + (int64_t)k * SCAN_THREADS + threadIdx.x;
-        if (i < n) s += (Tout)in[i];
-    }
-    s = warp_sum(s);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) sm[wid] = s;
-    __syncthreads();
-    if (wid == 0) {
-        Tout t = sm[lane];
-        t = warp_sum(t);
-        if (lane == 0) tile_sums[blockIdx.x] = t;
-    }
-}
 
 // tile_offsets == nullptr: single tile (n <= SCAN_TILE), writes out[n] = total itself.
 template <typename Tin, typename Tout>
@@ -62,7 +39,61 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_down_kernel(const Tin *__re
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = off + total;
 }
 
-// Exclusive scan; `out` needs n+1 elements.  In-place (out == in, same type) is allowed.
+// Single pass over the input with decoupled look-back (Merrill & Garland): a tile takes a ticket, publishes the sum
+// of its items, and the last thread walks back over its predecessors' (flag, value) words -- aggregate or inclusive
+// prefix, packed in one 64-bit word so that no fence is needed -- until it meets an inclusive prefix.  One launch and
+// 2 x 8 B/item of traffic instead of three launches (reduce / scan of sums / downsweep) and a second read.
+// status[0 .. ntiles): tile words, status[ntiles]: the ticket counter; zeroed before the launch.
+constexpr unsigned long long SCAN_AGG = 1ull << 62, SCAN_INC = 2ull << 62, SCAN_VAL = (1ull << 62) - 1ull;
+
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_lookback_kernel(const Tin *__restrict__ in, int64_t n, Tout *__restrict__ out,
+                                                                    unsigned long long *__restrict__ status, int ntiles) {
+    __shared__ Tout sm[33];
+    __shared__ unsigned long long s_tile, s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(status + ntiles, 1ull);
+    __syncthreads();
+    const int tile = (int)s_tile;
+    const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    Tout v[SCAN_ITEMS];
+    Tout s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const int64_t i = base + k;
+        v[k] = i < n ? (Tout)in[i] : Tout(0);
+        s += v[k];
+    }
+    Tout total;
+    Tout ex = block_exclusive_scan(s, sm, &total);
+    if (threadIdx.x == 0) {
+        volatile unsigned long long *st = status;
+        unsigned long long prefix = 0;
+        if (tile > 0) {
+            st[tile] = SCAN_AGG | ((unsigned long long)total & SCAN_VAL);
+            for (int j = tile - 1;; --j) {
+                unsigned long long w;
+                do { w = st[j]; } while ((w >> 62) == 0ull);
+                prefix += w & SCAN_VAL;
+                if ((w >> 62) == 2ull) break;
+            }
+        }
+        st[tile] = SCAN_INC | ((prefix + (unsigned long long)total) & SCAN_VAL);
+        s_prefix = prefix;
+    }
+    __syncthreads();
+    const Tout off = (Tout)s_prefix;
+    ex += off;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const int64_t i = base + k;
+        if (i < n) out[i] = ex;
+        ex += v[k];
+    }
+    if (tile == ntiles - 1 && threadIdx.x == 0) out[n] = off + total;
+}
+
+// Exclusive scan; `out` needs n+1 elements.  In-place (out == in, same type) is allowed.  Values are non-negative
+// and below 2^62.
 template <typename Tin, typename Tout>
 int exclusive_scan(const Tin *in, int64_t n, Tout *out, cudaStream_t st) {
     if (n <= 0) {
@@ -75,12 +106,10 @@ int exclusive_scan(const Tin *in, int64_t n, Tout *out, cudaStream_t st) {
         CRG_LAUNCH_CHECK();
         return CRG_OK;
     }
-    DevBuf<Tout> sums;
-    CRG_TRY(sums.alloc_tmp((size_t)ntiles + 1, st));
-    scan_reduce_kernel<Tin, Tout><<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(in, n, sums.p);
-    CRG_LAUNCH_CHECK();
-    CRG_TRY((exclusive_scan<Tout, Tout>(sums.p, ntiles, sums.p, st)));
-    scan_down_kernel<Tin, Tout><<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(in, n, sums.p, out);
+    DevBuf<unsigned long long> status;
+    CRG_TRY(status.alloc_tmp((size_t)ntiles + 1, st));
+    CRG_CUDA(cudaMemsetAsync(status.p, 0, sizeof(unsigned long long) * ((size_t)ntiles + 1), st));
+    scan_lookback_kernel<Tin, Tout><<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(in, n, out, status.p, (int)ntiles);
     CRG_LAUNCH_CHECK();
     return CRG_OK;
 }

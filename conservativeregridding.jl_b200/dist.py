@@ -267,7 +267,13 @@ class ShardedRegridder:
         self.src = src
         self.src_range = halo_range(block, src) if (halo and self.world > 1) else (0, self.n_src)
         self.local = factory(block, src.slice(*self.src_range) if self.src_range != (0, self.n_src) else src)
-        self._ranges = None           # every rank's halo range (collective, on first transpose)
+        # every rank's halo range: a function of the descriptors for described grids (computed locally, remembered),
+        # collective on the first transpose otherwise
+        self._ranges = None
+        if not (halo and self.world > 1):
+            self._ranges = [(0, self.n_src)] * self.world
+        elif isinstance(dst, GridSpec) and isinstance(src, GridSpec):
+            self._ranges = [halo_range(dst.slice(a, b), src) for a, b in self.dst_bounds]
         self._scale = None
         if normalize:
             # normalize!(R) (regridder.jl:54-62): A, dst_areas, src_areas ./= maximum(A); the maximum of a
@@ -390,11 +396,14 @@ class ShardedRegridder:
             return self._all_gather_blocks(out, self.dst_bounds) if gather else out
         y = field
         y_block = y if y.shape[0] == hi - lo and self.world > 1 else y[lo:hi]
+        # (the buffer is as long as the LONGEST halo, so that it can go into the all-gather as it is)
+        width = max(b - a for a, b in self._ranges) if (self._ranges is not None and gather and self.world > 1) else s_hi - s_lo
+        buf = torch.empty((width,) + tuple(y.shape[1:]), dtype=torch.float64, device=y.device)
+        part = buf[: s_hi - s_lo]
         if hi > lo and s_hi > s_lo:
-            part = torch.empty((s_hi - s_lo,) + tuple(y.shape[1:]), dtype=torch.float64, device=y.device)
             self.local.apply_T(part, y_block.contiguous(), normalize)
         else:
-            part = torch.zeros((s_hi - s_lo,) + tuple(y.shape[1:]), dtype=torch.float64, device=y.device)
+            part.zero_()
         if self.world == 1:
             if (s_lo, s_hi) == (0, self.n_src):
                 return part
@@ -406,13 +415,13 @@ class ShardedRegridder:
         # all-gather of the halo partials + overlap-add: no reduction collective (the halos of neighbouring
         # blocks share a few rings, everything else is written once)
         ranges = self.halo_ranges()
-        width = max(b - a for a, b in ranges)
-        pad = part
-        if part.shape[0] != width:
-            pad = torch.zeros((width,) + tuple(part.shape[1:]), dtype=torch.float64, device=part.device)
+        pad = buf
+        if buf.shape[0] != max(b - a for a, b in ranges):          # (ranges were not known before the apply)
+            width = max(b - a for a, b in ranges)
+            pad = torch.empty((width,) + tuple(part.shape[1:]), dtype=torch.float64, device=part.device)
             pad[: part.shape[0]] = part
         allp = torch.empty((self.world * width,) + tuple(part.shape[1:]), dtype=torch.float64, device=part.device)
-        dist.all_gather_into_tensor(allp, pad.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(allp, pad, group=self.group)
         # ranges of ring-major halos are increasing with the rank: block k is COPIED where nothing was written yet and
         # ADDED where it overlaps its predecessors; source cells no block reaches stay zero
         full = torch.empty((self.n_src,) + tuple(y.shape[1:]), dtype=torch.float64, device=y.device)
