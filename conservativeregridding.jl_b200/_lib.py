@@ -33,7 +33,7 @@ EXPORTS = [
     "crg_export_csc", "crg_export_csr", "crg_candidates", "crg_normalize", "crg_maximum", "crg_scale", "crg_apply", "crg_apply_async",
     "crg_set_stream", "crg_synchronize", "crg_apply_bytes", "crg_last_error", "crg_device_count", "crg_version",
     "crg_fp64_peak", "crg_launch_count", "crg_build_grids", "crg_grid_ncells", "crg_grid_cells",
-    "crg_clip_pairs", "crg_set_areas", "crg_grid_areas",
+    "crg_clip_pairs", "crg_set_areas", "crg_grid_areas", "crg_mirror_fold_partners",
 ]
 
 
@@ -126,6 +126,7 @@ def lib():
     L.crg_grid_ncells.argtypes = [P(GridDesc), P(i64)]
     L.crg_grid_cells.argtypes = [P(GridDesc), i32, vp]
     L.crg_grid_areas.argtypes = [P(Options), P(GridDesc), vp]
+    L.crg_mirror_fold_partners.argtypes = [vp, i64, i64, i64, i64, i32, i32, vp]
     L.crg_build_from_coo.argtypes = [P(Options), i64, i64, i64, vp, vp, vp, vp, vp, P(vp)]
     L.crg_free.argtypes = [vp]
     L.crg_dims.argtypes = [vp, P(i64), P(i64), P(i64)]

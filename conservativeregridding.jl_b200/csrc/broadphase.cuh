@@ -34,6 +34,7 @@ constexpr int BP_MAX_QUERY = 1 << 18;   // a destination cell covering more bins
 #ifndef BP_QUERY_MINB
 #define BP_QUERY_MINB 10
 #endif
+constexpr int BP_HEAVY = 256;           // a destination cell whose bins hold more entries than this is traversed by a whole warp
 constexpr int BP_SLAB = 32;             // candidates per destination cell kept by the count pass (slab[k][cell])
 constexpr int BP_SHORT_ROW = 48;        // rows with at most this many candidates are column-sorted by one thread
 constexpr double BP_BIG_ANGLE = 0.2;    // rad; larger spherical cells are "big"
@@ -312,6 +313,9 @@ __global__ void __launch_bounds__(256) bp_bin_kernel(CellsView g, const float *_
     int n;
     const double *p = stage_cell<DIM>(g, c, &n, stage);
     if (c >= g.ncells) return;
+    // a cell whose vertices all coincide is a GHOST (the padding polygon of a tripolar fold row): it has no area and
+    // is never a candidate, like the cells the reference keeps out of its tree (OceananigansExt.jl:66-75,141-160)
+    if (diam[c] == 0.f) return;
     bool big = DIM == 3 && !(diam[c] < (float)P.big_chord);
     if (DIM == 3 && !big) {
         const float x = (float)p[0], y = (float)p[1], z = (float)p[2];
@@ -376,12 +380,17 @@ __global__ void __launch_bounds__(128, BP_QUERY_MINB) bp_query_kernel(CellsView 
                                                        const int64_t *__restrict__ cand_off,
                                                        int2 *__restrict__ pairs, int32_t *__restrict__ big_dst,
                                                        uint32_t *__restrict__ big_dst_counter,
-                                                       int32_t *__restrict__ slab) {
+                                                       int32_t *__restrict__ slab, int32_t *__restrict__ heavy_list,
+                                                       uint32_t *__restrict__ heavy_counter) {
     __shared__ CellStage<DIM, 128> stage;
     const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int n;
     const double *p = stage_cell<DIM>(g, d, &n, stage);
     if (d >= g.ncells) return;
+    if (diam[d] == 0.f) {                    // ghost destination cell (see bp_bin_kernel): no candidates
+        if (!FILL) cand_count[d] = 0u;
+        return;
+    }
     bool big = DIM == 3 && !(diam[d] < (float)P.big_chord);
     QBox b;
     int f = 0;
@@ -405,6 +414,20 @@ __global__ void __launch_bounds__(128, BP_QUERY_MINB) bp_query_kernel(CellsView 
         return;
     }
     const int64_t nd = g.ncells;
+    // Where hundreds of source cells share a bin (the pole of a lon-lat source), one thread walking them all is the
+    // tail of the whole kernel (config 1: 0.57 of the 1.0 ms build): such cells go to a list and are traversed by a
+    // warp each in bp_query_heavy_kernel (the count pass decides; the fill pass skips them the same way).
+    if (heavy_list) {
+        uint32_t work = 0;
+        for (int by = b.y0 >> 4; by <= (b.y1 >> 4); ++by) {
+            const size_t row = ((size_t)f * P.nby + by) * P.nbx;
+            work += bin_start[row + (b.x1 >> 4) + 1] - bin_start[row + (b.x0 >> 4)];      // bins of a row are consecutive
+        }
+        if (work > (uint32_t)BP_HEAVY) {
+            if (!FILL) heavy_list[atomicAdd(heavy_counter, 1u)] = (int32_t)d;
+            return;
+        }
+    }
     uint32_t cnt = 0;
     int2 *out = FILL ? pairs + cand_off[d] : nullptr;
     for (int by = b.y0 >> 4; by <= (b.y1 >> 4); ++by)
@@ -432,6 +455,72 @@ __global__ void __launch_bounds__(128, BP_QUERY_MINB) bp_query_kernel(CellsView 
         cand_count[d] = cnt;
         if (cnt > BP_SHORT_ROW) big_dst_counter[1] = 1u;      // flag: some row is long (benign race, same value)
         if (cnt > BP_SLAB) big_dst_counter[2] = 1u;           // flag: the slab does not hold every candidate
+    }
+}
+
+// One WARP per heavy destination cell (see bp_query_kernel): the lanes stride over the entries of its bins; a ballot
+// ranks the candidates, so the list order is the order of the entries (deterministic).
+template <int DIM, bool FILL>
+__global__ void __launch_bounds__(128) bp_query_heavy_kernel(CellsView g, BPParams P, const uint32_t *__restrict__ bin_start,
+                                                             const int4 *__restrict__ entries,
+                                                             const int32_t *__restrict__ big_src, int n_big_src,
+                                                             uint32_t *__restrict__ cand_count,
+                                                             const int64_t *__restrict__ cand_off, int2 *__restrict__ pairs,
+                                                             uint32_t *__restrict__ flags /* [1] long row, [2] slab overflow */,
+                                                             int32_t *__restrict__ slab, const int32_t *__restrict__ heavy_list,
+                                                             const uint32_t *__restrict__ heavy_counter) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t nheavy = *heavy_counter;
+    const int64_t nd = g.ncells;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (uint32_t h = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); h < nheavy; h += gridDim.x * (blockDim.x >> 5)) {
+        const int64_t d = heavy_list[h];
+        int n;
+        const double *p = cell_ptr<DIM>(g, d, &n);
+        const int f = DIM == 3 ? home_face(p, n) : 0;
+        QBox b;
+        bool cl = false;
+        cell_face_qbox<DIM>(p, n, f, P, &b, &cl);            // (accepted by bp_query_kernel already)
+        uint32_t cnt = 0;
+        int2 *out = FILL ? pairs + cand_off[d] : nullptr;
+        for (int by = b.y0 >> 4; by <= (b.y1 >> 4); ++by)
+            for (int bx = b.x0 >> 4; bx <= (b.x1 >> 4); ++bx) {
+                const size_t bin = ((size_t)f * P.nby + by) * P.nbx + bx;
+                const uint32_t lo = bin_start[bin], hi = bin_start[bin + 1];
+                for (uint32_t k0 = lo; k0 < hi; k0 += 32) {
+                    const uint32_t k = k0 + lane;
+                    bool hit = false;
+                    int src = 0;
+                    if (k < hi) {
+                        const int4 e = __ldg(&entries[k]);
+                        const int sx0 = e.y & 0xffff, sx1 = (e.y >> 16) & 0xffff;
+                        const int sy0 = e.z & 0xffff, sy1 = (e.z >> 16) & 0xffff;
+                        hit = !(sx0 > b.x1 || b.x0 > sx1 || sy0 > b.y1 || b.y0 > sy1) &&
+                              (max(sx0, b.x0) >> 4) == bx && (max(sy0, b.y0) >> 4) == by;
+                        src = e.x;
+                    }
+                    const unsigned m = __ballot_sync(CRG_FULL, hit);
+                    if (hit) {
+                        const uint32_t pos = cnt + __popc(m & lt);
+                        if (FILL) out[pos] = make_int2(src, (int)d);
+                        else if (slab && pos < (uint32_t)BP_SLAB) slab[(size_t)pos * nd + d] = src;
+                    }
+                    cnt += __popc(m);
+                }
+            }
+        for (int k0 = 0; k0 < n_big_src; k0 += 32) {
+            const int k = k0 + lane;
+            if (k < n_big_src) {
+                if (FILL) out[cnt + k] = make_int2(big_src[k], (int)d);
+                else if (slab && cnt + k < (uint32_t)BP_SLAB) slab[(size_t)(cnt + k) * nd + d] = big_src[k];
+            }
+        }
+        cnt += (uint32_t)n_big_src;
+        if (!FILL && lane == 0) {
+            cand_count[d] = cnt;
+            if (cnt > BP_SHORT_ROW) flags[1] = 1u;
+            if (cnt > BP_SLAB) flags[2] = 1u;
+        }
     }
 }
 

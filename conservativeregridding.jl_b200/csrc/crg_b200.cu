@@ -145,6 +145,18 @@ __global__ void __launch_bounds__(256) scale_kernel(double *v, int64_t n, double
     if (i < n) v[i] *= f;
 }
 
+// mirror_fold_partners! of the reference's Oceananigans extension (a KernelAbstractions kernel over 2 Nq slots there)
+__global__ void __launch_bounds__(128) mirror_fold_kernel(double *__restrict__ f, int64_t nx, int64_t ny, int64_t K,
+                                                          int64_t ld, int level_fastest) {
+    const int64_t nq = nx / 4, nh = nx / 2, base = (ny - 1) * nx;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * nq * K) return;
+    const int64_t k = level_fastest ? t % K : t / (2 * nq), i = level_fastest ? t / K : t % (2 * nq);
+    const int64_t r = i < nq ? i : nh + (i - nq), q = nx - 1 - r;
+    if (level_fastest) f[(base + q) * ld + k] = f[(base + r) * ld + k];
+    else f[k * ld + base + q] = f[k * ld + base + r];
+}
+
 static int stage_cells(const crg_cells *c, int dim, cudaStream_t st, DevCells *out, const char *name) {
     const int64_t n = c->ncells;
     out->view.ncells = n;
@@ -741,10 +753,23 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     DevBuf<int32_t> slab;
     static const bool allow_slab = !(getenv("CRG_QUERY_SLAB") && atoi(getenv("CRG_QUERY_SLAB")) == 0);
     if (allow_slab && nd) CRG_TRY(slab.alloc_tmp((size_t)BP_SLAB * nd, st));
+    DevBuf<int32_t> heavy_list;
+    DevBuf<uint32_t> heavy_counter;
+    static const bool allow_heavy = !(getenv("CRG_QUERY_HEAVY") && atoi(getenv("CRG_QUERY_HEAVY")) == 0);
+    CRG_TRY(heavy_counter.alloc_tmp(1, st));
+    CRG_CUDA(cudaMemsetAsync(heavy_counter.p, 0, sizeof(uint32_t), st));
+    if (allow_heavy && nd) CRG_TRY(heavy_list.alloc_tmp((size_t)nd, st));
+    constexpr int HEAVY_GRID = 148 * 4;
     if (nd) bp_query_kernel<DIM, false><<<ceil_div(nd, 128), 128, 0, st>>>(
         gd.view, gd.diam.p, P, bin_start.p, entries.p, big_src.p, n_big_src, ns, cand_count.p, nullptr, nullptr,
-        big_dst.p, counters.p + 1, slab.p);
+        big_dst.p, counters.p + 1, slab.p, heavy_list.p, heavy_counter.p);
     if (nd) CRG_LAUNCH_CHECK();
+    if (nd && heavy_list.p) {
+        bp_query_heavy_kernel<DIM, false><<<HEAVY_GRID, 128, 0, st>>>(gd.view, P, bin_start.p, entries.p, big_src.p, n_big_src,
+                                                                     cand_count.p, nullptr, nullptr, counters.p + 1, slab.p,
+                                                                     heavy_list.p, heavy_counter.p);
+        CRG_LAUNCH_CHECK();
+    }
     CRG_TRY((exclusive_scan<uint32_t, int64_t>(cand_count.p, nd, cand_off.p, st)));
     int64_t n_cand = 0;
     CRG_CUDA(cudaMemcpyAsync(&n_cand, cand_off.p + nd, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -765,7 +790,13 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     } else if (nd) {
         bp_query_kernel<DIM, true><<<ceil_div(nd, 128), 128, 0, st>>>(
             gd.view, gd.diam.p, P, bin_start.p, entries.p, big_src.p, n_big_src, ns, nullptr, cand_off.p, pairs.p, nullptr,
-            nullptr, nullptr);
+            nullptr, nullptr, heavy_list.p, heavy_counter.p);
+        if (heavy_list.p) {
+            CRG_LAUNCH_CHECK();
+            bp_query_heavy_kernel<DIM, true><<<HEAVY_GRID, 128, 0, st>>>(gd.view, P, bin_start.p, entries.p, big_src.p, n_big_src,
+                                                                        nullptr, cand_off.p, pairs.p, nullptr, nullptr,
+                                                                        heavy_list.p, heavy_counter.p);
+        }
     }
     if (nd) CRG_LAUNCH_CHECK();
     if (n_big_dst && ns) {
@@ -1608,6 +1639,36 @@ int crg_apply(crg_regridder *r, int32_t transpose, int32_t divide, double *dst, 
 int crg_apply_async(crg_regridder *r, int32_t transpose, int32_t divide, double *dst, const double *src, int64_t K,
                     int64_t ld_dst, int64_t ld_src, int32_t level_fastest) {
     return apply_impl(r, transpose, divide, dst, src, K, ld_dst, ld_src, level_fastest, false, false);
+}
+
+int crg_mirror_fold_partners(double *field, int64_t nx, int64_t ny, int64_t K, int64_t ld, int32_t level_fastest,
+                             int32_t device, void *stream) {
+    if (!field) return set_error(CRG_ERR_INVALID, "crg_mirror_fold_partners: null field");
+    if (nx < 4 || (nx & 3) || ny < 1 || K < 1) return set_error(CRG_ERR_INVALID, "crg_mirror_fold_partners: nx must be a positive multiple of 4, ny and K positive");
+    const int64_t n = nx * ny;
+    if (K == 1 && ld <= 0) ld = level_fastest ? 1 : n;
+    if (level_fastest ? ld < K : ld < n) return set_error(CRG_ERR_INVALID, "crg_mirror_fold_partners: leading dimension %lld too small", (long long)ld);
+    const int64_t nq = nx / 4, nh = nx / 2, base = (ny - 1) * nx;
+    if (!is_device_ptr(field)) {
+        for (int64_t k = 0; k < K; ++k)
+            for (int64_t i = 0; i < 2 * nq; ++i) {
+                const int64_t r = i < nq ? i : nh + (i - nq), q = nx - 1 - r;
+                if (level_fastest) field[(base + q) * ld + k] = field[(base + r) * ld + k];
+                else field[k * ld + base + q] = field[k * ld + base + r];
+            }
+        return CRG_OK;
+    }
+    CRG_TRY(check_device_available());
+    DeviceGuard guard;
+    CRG_TRY(guard.set(device));
+    int dev = 0;
+    CRG_CUDA(cudaGetDevice(&dev));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!st) CRG_TRY(device_stream(dev, &st));
+    mirror_fold_kernel<<<ceil_div(2 * nq * K, 128), 128, 0, st>>>(field, nx, ny, K, ld, level_fastest);
+    CRG_LAUNCH_CHECK();
+    if (!stream) CRG_CUDA(cudaStreamSynchronize(st));
+    return CRG_OK;
 }
 
 int crg_set_stream(crg_regridder *r, void *s) {

@@ -548,6 +548,54 @@ def octahedral_gaussian_grid(nlat_half: int, radius: float = 1.0) -> Grid:
 
 
 # ----------------------------------------------------------------------------
+# tripolar fold (Oceananigans RightCenterFolded)
+# ----------------------------------------------------------------------------
+
+def fold_row_slots(nx: int):
+    """0-based local indices along the fold row of a ``RightCenterFolded`` grid: ``(real, partner)`` with
+    ``partner[k] = nx - 1 - real[k]`` -- the reference's partition: real locals 1..Nq and Nh+1..Nh+Nq (1-based),
+    the partner of r is Nx+1-r (ext/ConservativeRegriddingOceananigansExt.jl:119-187,216-240)."""
+    nh, nq = nx // 2, nx // 4
+    real = np.concatenate([np.arange(nq), nh + np.arange(nq)]).astype(np.int64)
+    return real, nx - 1 - real
+
+
+def tripolar_fold_grid(nx: int, ny: int, lat_south: float = -80.0, lat_fold: float = 84.0, radius: float = 1.0) -> Grid:
+    """Synthetic stand-in of an Oceananigans ``TripolarGrid`` with a ``RightCenterFolded`` north row, cells exactly as
+    ``Trees.treeify`` makes them (OceananigansExt.jl:76-187): an (nx+1) x (ny+1) vertex matrix, cell (i, j) at field
+    index i + j nx; rows 0 .. ny-2 are lon-lat bands from ``lat_south`` to ``lat_fold``; the LAST row covers the cap
+    north of ``lat_fold`` by strips across it, vertex (i, ny) = vertex (nx - i, ny - 1), so that fold-row cell i is the
+    same physical quadrilateral as cell nx - 1 - i -- the fold.  Of every such pair one slot carries the polygon and
+    its partner is a ghost: a degenerate ring of four equal points (zero area, no overlaps), like the reference's
+    ``PaddedTreeWrapper``.  ``regrid!`` then copies each primary's value into its partner
+    (:func:`mirror_fold_partners`)."""
+    assert nx % 4 == 0 and ny >= 2
+    lon = 360.0 * np.arange(nx + 1) / nx
+    lat = lat_south + (lat_fold - lat_south) * np.arange(ny) / (ny - 1)        # vertex rows 0 .. ny-1
+    P = np.empty((nx + 1, ny + 1, 3))
+    P[:, :ny] = unit_sphere_from_geographic(lon[:, None], lat[None, :])
+    P[:, ny] = P[::-1, ny - 1]                                                 # the fold
+    cells = cells_from_vertex_matrix(P)                                        # [ny * nx, 4, 3], i fastest
+    real, partner = fold_row_slots(nx)
+    ghost = np.ones(nx, dtype=bool); ghost[real] = False
+    base = (ny - 1) * nx
+    cells[base + np.nonzero(ghost)[0]] = P[0, ny - 1]                          # ghost_polygon: p, p, p, p
+    g = Grid(np.ascontiguousarray(cells), SPHERICAL, None, radius, f"tripolar{nx}x{ny}")
+    g.meta.update(kind="tripolar_fold", shape=(nx, ny), fold=(nx, ny))
+    return g
+
+
+def mirror_fold_partners(field, nx: int, ny: int, axis: int = 0):
+    """``mirror_fold_partners!`` (OceananigansExt.jl:216-240) on a host array: along ``axis`` (the cells) the value of
+    every primary of the fold row is copied into its partner slot.  In place; returns ``field``."""
+    real, partner = fold_row_slots(nx)
+    base = (ny - 1) * nx
+    v = np.moveaxis(field, axis, 0)
+    v[base + partner] = v[base + real]
+    return field
+
+
+# ----------------------------------------------------------------------------
 # cell centres (for sampling analytic fields)
 # ----------------------------------------------------------------------------
 

@@ -298,8 +298,11 @@ class RegridderB200:
     """``Regridder{W,A,V}`` (regridder.jl:25-36).  The area vectors are fetched from the device on
     first access and the work vectors allocated on first use; transpose(R) shares the same objects."""
 
-    def __init__(self, intersections: B200Matrix, dst_areas, src_areas, dst_temp, src_temp):
+    def __init__(self, intersections: B200Matrix, dst_areas, src_areas, dst_temp, src_temp, dst_fold=None, src_fold=None):
         self.intersections = intersections
+        # (nx, ny) of a tripolar destination / source grid with a RightCenterFolded north row: regrid! mirrors the fold
+        # partners of its result (finalize_regridding! of the Oceananigans extension, OceananigansExt.jl:206-240)
+        self.dst_fold, self.src_fold = dst_fold, src_fold
         wrap = lambda v: v if isinstance(v, _Lazy) else _Lazy(lambda v=v: v)  # noqa: E731
         self._dst_areas, self._src_areas = wrap(dst_areas), wrap(src_areas)
         self._dst_temp, self._src_temp = wrap(dst_temp), wrap(src_temp)
@@ -327,7 +330,7 @@ class RegridderB200:
 
 def transpose(R: RegridderB200) -> RegridderB200:
     """``LinearAlgebra.transpose(::Regridder)``: no copy, areas and temps swapped (regridder.jl:49-50)."""
-    return RegridderB200(R.intersections.T, R._src_areas, R._dst_areas, R._src_temp, R._dst_temp)
+    return RegridderB200(R.intersections.T, R._src_areas, R._dst_areas, R._src_temp, R._dst_temp, R.src_fold, R.dst_fold)
 
 
 def _refresh_areas(R: RegridderB200):
@@ -413,6 +416,36 @@ def _host_empty(n: int) -> np.ndarray:
     return np.empty(n)
 
 
+def _fold_of(g):
+    return tuple(g.meta["fold"]) if isinstance(g, Grid) and g.meta.get("fold") else None
+
+
+def mirror_fold_partners_(field, fold, *, dims: int = 0):
+    """``mirror_fold_partners!`` (OceananigansExt.jl:216-240) on a numpy array or a CUDA tensor whose axis ``dims``
+    runs over the nx * ny cells of a folded grid (``fold = (nx, ny)``): in place, a tiny kernel for device fields."""
+    nx, ny = fold
+    lay = _layout(field, dims, nx * ny)
+    if lay is None or (not _is_torch(field) and field.dtype != np.float64) or \
+            (_is_torch(field) and str(field.dtype) != "torch.float64"):
+        if _is_torch(field):
+            import torch
+            from .grids import fold_row_slots
+            real, partner = fold_row_slots(nx)
+            base = (ny - 1) * nx
+            v = field.movedim(dims, 0)
+            v[torch.as_tensor(base + partner, device=field.device)] = v[torch.as_tensor(base + real, device=field.device)]
+            return field
+        from .grids import mirror_fold_partners
+        return mirror_fold_partners(field, nx, ny, axis=dims)
+    K, ld, lf = lay
+    dev, stream = -1, None
+    if _is_torch(field) and field.is_cuda:
+        dev, stream = field.device.index, torch_stream_ptr(field.device)
+    _lib.check(_lib.lib().crg_mirror_fold_partners(C.c_void_p(_ptr(field)), nx, ny, K, ld, int(lf), dev,
+                                                  C.c_void_p(stream) if stream else None))
+    return field
+
+
 def _wrap(ptr, n_dst, n_src, stream=None) -> RegridderB200:
     h = _Handle(ptr, stream)
     M = B200Matrix(h, n_dst, n_src)
@@ -431,7 +464,16 @@ def _wrap(ptr, n_dst, n_src, stream=None) -> RegridderB200:
                          _Lazy(lambda: np.zeros(n_src)))
 
 
-def Regridder(dst, src, *, manifold: Optional[int] = None, normalize: bool = False,
+def Regridder(dst, src, **kw) -> RegridderB200:
+    """``Regridder(dst, src; normalize=false, intersection_operator, threaded, ...)`` (regridder.jl:105-163); keywords
+    and behaviour: see :func:`_regridder`.  A grid with a tripolar fold row (``tripolar_fold_grid``) is remembered, so
+    that ``regrid!`` mirrors the fold partners of its result like the Oceananigans extension does."""
+    R = _regridder(dst, src, **kw)
+    R.dst_fold, R.src_fold = _fold_of(dst), _fold_of(src)
+    return R
+
+
+def _regridder(dst, src, *, manifold: Optional[int] = None, normalize: bool = False,
               intersection_operator: Optional[Callable] = None, threaded=True, radius: Optional[float] = None,
               device: Optional[int] = None, area_threshold: float = 0.0, build_transpose: bool = True,
               keep_candidates: bool = False, stream: Optional[int] = None, **_ignored) -> RegridderB200:
@@ -577,6 +619,16 @@ def _ptr(a) -> int:
 
 
 def regrid_(dst_field, R: RegridderB200, src_field, *, dims: int = 0, normalize: bool = True,
+            asynchronous: bool = False):
+    """``regrid!`` (see :func:`_regrid`) + ``mirror_fold_partners!`` when the destination grid has a tripolar fold
+    row (``finalize_regridding!`` of the Oceananigans extension, OceananigansExt.jl:206-214)."""
+    out = _regrid(dst_field, R, src_field, dims=dims, normalize=normalize, asynchronous=asynchronous)
+    if R.dst_fold is not None:
+        mirror_fold_partners_(out, R.dst_fold, dims=dims if out.ndim > 1 else 0)
+    return out
+
+
+def _regrid(dst_field, R: RegridderB200, src_field, *, dims: int = 0, normalize: bool = True,
             asynchronous: bool = False):
     """``regrid!(dst_field, regridder, src_field; dims, normalize)`` (regrid.jl:63-118,205-318).
 

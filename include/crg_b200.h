@@ -214,6 +214,16 @@ int crg_apply_async(crg_regridder *r, int32_t transpose, int32_t divide_by_area,
                     const double *src, int64_t K, int64_t ld_dst, int64_t ld_src,
                     int32_t level_fastest);
 
+/* mirror_fold_partners! (ext/ConservativeRegriddingOceananigansExt.jl:216-240): on a tripolar grid with a
+ * RightCenterFolded north row (nx x ny cells, field index i + j * nx) every physical cell of the last row shows
+ * up at two field slots; one carries the polygon, its partner is a zero-area ghost whose matrix row is empty.
+ * After regrid! the value of every primary slot r (0-based: 0 .. nx/4-1 and nx/2 .. nx/2+nx/4-1) is copied into
+ * its partner nx-1-r.  `field`: K fields laid out like crg_apply's dst (ld, level_fastest); device pointer: a
+ * kernel on `stream` (NULL = the library stream of `device`, synchronised before returning); host pointer: copied
+ * in place on the host.                                                                                       */
+int crg_mirror_fold_partners(double *field, int64_t nx, int64_t ny, int64_t K, int64_t ld, int32_t level_fastest,
+                             int32_t device, void *stream);
+
 /* Run the handle's work on a caller-owned cudaStream_t (e.g. torch's current stream).
  * NULL restores the handle's own (non-blocking) stream; the legacy default stream is named
  * explicitly as cudaStreamLegacy ((cudaStream_t)0x1), the per-thread one as cudaStreamPerThread

@@ -272,12 +272,30 @@ def coo_to_csc(n_rows, n_cols, rows, cols, vals):
     return colptr, rowval[:m].copy(), nzval[:m].copy()
 
 
+def _ghost_cells(grid):
+    """Mask of the cells whose vertices all coincide (fixed-size rings), or None when there are none."""
+    if grid.offsets is not None or grid.ncells == 0:
+        return None
+    g = (grid.verts == grid.verts[:, :1]).all(axis=(1, 2))
+    return g if g.any() else None
+
+
 def build_regridder(dst, src, normalize=False, candidates=None, nthreads=1) -> OracleRegridder:
     """``Regridder(manifold, dst, src; normalize)`` (regridder.jl:125-163)."""
     assert dst.manifold == src.manifold
     if candidates is None:
         candidates = candidate_pairs_safe(dst, src)
     ps, pd = candidates
+    # ghost cells (a ring of equal points: the padding polygon of a tripolar fold row) are not in the reference's
+    # spatial tree and hence never candidates (ext/ConservativeRegriddingOceananigansExt.jl:66-75,141-160)
+    gd, gs = _ghost_cells(dst), _ghost_cells(src)
+    if gd is not None or gs is not None:
+        keep = np.ones(len(ps), dtype=bool)
+        if gd is not None:
+            keep &= ~gd[pd]
+        if gs is not None:
+            keep &= ~gs[ps]
+        ps, pd = ps[keep], pd[keep]
     i1, i2, a = compute_intersection_areas(dst, src, ps, pd, nthreads)
     r2 = dst.radius ** 2 if dst.manifold else 1.0
     a = a * r2

@@ -44,9 +44,13 @@ def sass_thread_ops(path, kernel_substr):
     """Predicated-on THREAD instruction counts by opcode from the SASS page of one kernel of the report."""
     out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    ops, cur, hdr = {}, None, None
+    ops, cur, hdr, seen = {}, None, None, 0
     for r in rows:
-        if len(r) >= 2 and r[0] in ("Function Name", "Kernel Name"): cur = r[1]; continue
+        if len(r) >= 2 and r[0] in ("Function Name", "Kernel Name"):
+            cur = r[1]
+            seen += kernel_substr in cur          # (the page lists every kernel once per view: count the first listing only)
+            if seen > 1 and kernel_substr in cur: cur = None
+            continue
         if r and r[0] == "Address": hdr = r; continue
         if hdr and cur and kernel_substr in cur and len(r) == len(hdr):
             d = dict(zip(hdr, r))

@@ -516,3 +516,59 @@ def test_clip_pairs_matches_the_build_and_the_oracle(gpu):
     assert np.array_equal(clip_pairs(g1, g2, kk[:, 0], kk[:, 1]).reshape(4, 5), KAT_MATRIX)
     with pytest.raises(_lib.CrgError):
         clip_pairs(dst, src, [src.ncells], [0])
+
+
+def test_tripolar_fold_row_ghost_cells_and_mirroring(gpu):
+    """a tripolar grid with a RightCenterFolded north row (ext/ConservativeRegriddingOceananigansExt.jl:
+    76-187): every physical cell of the fold row has two field slots, one real and one ghost (zero area, never a
+    candidate); regrid! copies each primary's value into its partner (:216-240).  Checked against the oracle with the
+    same padding semantics, in both directions, plus the reference's own invariants for tripolar grids
+    (test/usecases/constant_field.jl:41-155 ones -> ones, test/usecases/oceananigans.jl:37-159 conservation 1e-10)."""
+    import torch
+    oracle = _oracle()
+    nx, ny = 64, 24
+    tri = grids.tripolar_fold_grid(nx, ny)
+    real, partner = grids.fold_row_slots(nx)
+    base = (ny - 1) * nx
+    for other in (grids.healpix_grid(16, "ring"), grids.lonlat_grid(72, 36)):
+        # tripolar as destination
+        R = Regridder(tri, other)
+        O = oracle.build_regridder(tri, other, nthreads=oracle.max_threads())
+        compare_matrices(R.intersections.tocsc(), O.tocsc(), O.dst_areas, O.src_areas)
+        assert np.allclose(R.dst_areas, O.dst_areas, rtol=1e-13, atol=0) and (R.dst_areas[base + partner] == 0).all()
+        A = R.intersections.tocsr()
+        assert np.diff(A.indptr)[base + partner].sum() == 0                   # ghost rows are empty
+        assert R.dst_fold == (nx, ny) and R.src_fold is None and transpose(R).src_fold == (nx, ny)
+        x = np.random.default_rng(3).random(other.ncells)
+        y = np.zeros(tri.ncells); regrid_(y, R, x)
+        want = grids.mirror_fold_partners(O.regrid(x), nx, ny)
+        assert np.isfinite(y).all() and np.allclose(y, want, rtol=1e-12)
+        assert np.array_equal(y[base + partner], y[base + real])              # partners mirror their primaries
+        ones = np.zeros(tri.ncells); regrid_(ones, R, np.ones(other.ncells))
+        assert np.allclose(ones, 1.0, atol=1e-10)
+        # device tensors (the mirror kernel), single field and K levels in both layouts
+        yd = torch.zeros(tri.ncells, dtype=torch.float64, device="cuda")
+        regrid_(yd, R, torch.from_numpy(x).cuda())
+        assert np.array_equal(yd.cpu().numpy(), y)
+        X = np.random.default_rng(4).random((other.ncells, 3))
+        for order in ("C", "F"):
+            Yd = torch.zeros(tri.ncells, 3, dtype=torch.float64, device="cuda")
+            if order == "F":
+                Yd = Yd.T.contiguous().T
+            Xd = torch.from_numpy(np.asarray(X, order=order)).cuda()
+            Xd = Xd if order == "C" else torch.from_numpy(np.ascontiguousarray(X.T)).cuda().T
+            regrid_(Yd, R, Xd, dims=0)
+            got = Yd.cpu().numpy()
+            assert np.allclose(got[:, 0], grids.mirror_fold_partners(O.regrid(X[:, 0].copy()), nx, ny), rtol=1e-12)
+            assert np.array_equal(got[base + partner], got[base + real])
+        # tripolar as source: ghost columns are empty, the integral is conserved on the covered part
+        RT = Regridder(other, tri)
+        OT = oracle.build_regridder(other, tri, nthreads=oracle.max_threads())
+        compare_matrices(RT.intersections.tocsc(), OT.tocsc(), OT.dst_areas, OT.src_areas)
+        xs = grids.mirror_fold_partners(np.random.default_rng(5).random(tri.ncells), nx, ny)
+        yo = np.zeros(other.ncells); regrid_(yo, RT, xs, normalize=False)
+        assert abs(yo.sum() / (xs * RT.src_areas).sum() - 1) < 1e-10
+        # transpose(R) of the first regridder regrids back ONTO the tripolar grid: mirrored as well
+        back = np.zeros(other.ncells); regrid_(back, transpose(R), y)
+        onto = np.zeros(tri.ncells); regrid_(onto, transpose(RT), yo)
+        assert np.array_equal(onto[base + partner], onto[base + real])

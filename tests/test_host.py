@@ -1,4 +1,6 @@
 """CPU tests of the host-side logic: grid generators, field layouts, dims validation."""
+import os
+
 import numpy as np
 import pytest
 
@@ -152,3 +154,29 @@ def test_kernel_counters_match_the_shipped_sources():
     for name, e in d.items():
         assert e["src_hash"] == bench.source_hash(e["src_files"]), f"{name}: kernel sources changed since the ncu capture"
     assert 100 < d["clip"]["flops_per_pair"] < 2000
+
+
+def test_tripolar_fold_grid_structure():
+    """The synthetic RightCenterFolded grid: fold-row cell i is the same quadrilateral as cell nx-1-i; of each pair one
+    slot is real and its partner a zero-area ghost (OceananigansExt.jl:119-160); the oracle keeps ghosts out of the
+    candidates, so their rows / columns are empty and ones -> ones after mirroring."""
+    nx, ny = 32, 10
+    g = grids.tripolar_fold_grid(nx, ny)
+    real, partner = grids.fold_row_slots(nx)
+    assert sorted(np.concatenate([real, partner]).tolist()) == list(range(nx))
+    assert real.tolist() == list(range(8)) + list(range(16, 24)) and (partner == nx - 1 - real).all()
+    base = (ny - 1) * nx
+    assert (g.verts[base + partner] == g.verts[base + partner][:, :1]).all()           # ghosts: four equal points
+    # the real cell r and the cell the fold maps it to are the same polygon (checked on the vertex matrix rule)
+    lon = 360.0 * np.arange(nx + 1) / nx
+    top = grids.unit_sphere_from_geographic(lon, np.full(nx + 1, 84.0))
+    for r in real:
+        assert np.allclose(g.verts[base + r], [top[r], top[r + 1], top[nx - r - 1], top[nx - r]], atol=1e-15)
+    a = oracle.cell_areas(g)
+    assert (a[base + partner] == 0).all() and (a[base + real] > 0).all()
+    assert abs(a.sum() / (2 * np.pi * (1 - np.sin(np.radians(-80.0)))) - 1) < 1e-3      # the real cells tile the cap once
+    src = grids.healpix_grid(8, "ring")
+    O = oracle.build_regridder(g, src)
+    assert np.diff(O.tocsc().tocsr().indptr)[base + partner].sum() == 0
+    y = grids.mirror_fold_partners(O.regrid(np.ones(src.ncells)), nx, ny)
+    assert np.allclose(y, 1.0, atol=1e-10)
