@@ -74,3 +74,67 @@ def test_product_package_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
                 txt = open(os.path.join(root, f)).read()
                 assert "oracle" not in txt.lower().replace("no cpu fallback", ""), os.path.join(root, f)
+
+
+# --- the Julia binding (untestable here: no Julia in the image) is at least held to the header ----------------------
+JL = os.path.join(os.path.dirname(HEADER), "..", "conservativeregridding.jl_b200", "julia", "CRGB200.jl")
+JL_SIZES = {"Int32": 4, "Int64": 8, "Float64": 8, "Ptr{Cvoid}": 8, "Ptr{Float64}": 8, "Ptr{Int32}": 8,
+            "NTuple{4, Float64}": 32, "CrgCells": 32}
+JL_ALIGN = {"NTuple{4, Float64}": 8, "CrgCells": 8}
+
+
+def julia_structs():
+    src = open(JL).read()
+    out = {}
+    for name, body in re.findall(r"^struct (Crg\w+)[^\n]*\n(.*?)^end", src, flags=re.S | re.M):
+        out[name] = [(f, t.strip()) for f, t in re.findall(r"^\s+(\w+)::([^#\n]+)", body, flags=re.M)]
+    return out
+
+
+def layout(fields):
+    off, offs = 0, []
+    for _, t in fields:
+        size, align = JL_SIZES[t], JL_ALIGN.get(t, JL_SIZES[t])
+        off = (off + align - 1) // align * align
+        offs.append((off, size))
+        off += size
+    return offs, (off + 7) // 8 * 8
+
+
+def test_julia_struct_layouts_match_the_ctypes_mirror_and_header():
+    js = julia_structs()
+    for jl_name, ct in (("CrgOptions", _lib.Options), ("CrgCells", _lib.Cells), ("CrgGrid", _lib.GridDesc)):
+        fields = js[jl_name]
+        assert [f for f, _ in fields] == [f for f, _ in ct._fields_], jl_name          # same names, same order
+        offs, total = layout(fields)
+        assert total == C.sizeof(ct), (jl_name, total, C.sizeof(ct))
+        for (f, _), (o, sz) in zip(fields, offs):
+            d = getattr(ct, f)
+            assert (d.offset, d.size) == (o, sz), (jl_name, f, (d.offset, d.size), (o, sz))
+    # and the header's struct bodies list the same fields in the same order
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    for c_name, ct in (("crg_options", _lib.Options), ("crg_cells", _lib.Cells), ("crg_grid", _lib.GridDesc),
+                       ("crg_build_stats", _lib.BuildStats)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (c_name, c_name), hdr, flags=re.S).group(1)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):
+                names.append(re.sub(r"\[.*?\]", "", part.strip().split()[-1].lstrip("*")))
+        assert names == [f for f, _ in ct._fields_], (c_name, names)
+
+
+def test_julia_ccalls_name_declared_symbols_with_the_right_arity():
+    src = open(JL).read()
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    arity = {}
+    for name, args in re.findall(r"\b(crg_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr):
+        arity[name] = 0 if args.strip() in ("", "void") else len(args.split(","))
+    calls = re.findall(r"ccall\(\(:(crg_\w+), lib\), \w+,\s*\(([^()]*)\)", src, flags=re.S)
+    assert len(calls) >= 10
+    for name, sig in calls:
+        assert name in arity, name
+        n = 0 if not sig.strip() else len([a for a in re.split(r",(?![^{]*\})", sig) if a.strip()])
+        assert n == arity[name], (name, n, arity[name], sig)
