@@ -573,7 +573,20 @@ static int launch_clip(const CellsView &gdv, const CellsView &gsv, bool fixed, i
         CRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
         kern<<<ceil_div(n_cand, NT_), NT_, smem, st>>>(gdv, gsv, pairs, n_cand, thresh, pair_area, tile_count);       \
     } while (0)
-    if (quad) {
+    static const bool allow_fast = getenv("CRG_CLIP_FAST") && atoi(getenv("CRG_CLIP_FAST")) != 0;   // opt-in: measured slower than clip_quad_kernel overall (profiles/README.md)
+    if (quad && DIM == 3 && allow_fast) {
+        // Spherical quadrilaterals: wedge sums for the pairs cut by one edge or two adjacent ones, symbolic
+        // Sutherland-Hodgman for the rest, one kernel (kernels.cuh).
+        DevBuf<double> nrm, corners;
+        CRG_TRY(nrm.alloc_tmp((size_t)gdv.ncells * 12, st));
+        CRG_TRY(corners.alloc_tmp((size_t)gdv.ncells * 12, st));
+        quad_normals_kernel<<<ceil_div(gdv.ncells, 256), 256, 0, st>>>(gdv, nrm.p, corners.p);
+        CRG_LAUNCH_CHECK();
+        const int grid = ceil_div(ceil_div(n_cand, CF_CHUNK), CF_NT / 32);
+        const size_t smem = (size_t)(CF_NT / 32) * CF_WARP_SMEM;
+        clip_quad_fast_kernel<<<grid, CF_NT, smem, st>>>(gdv, gsv, nrm.p, corners.p, pairs, n_cand, thresh, unit_src_areas, pair_area,
+                                                         tile_count);
+    } else if (quad) {
         constexpr int NT = 128;
         const size_t smem = sizeof(double) * QUAD_SLOTS * DIM * NT;
         auto kern = clip_quad_kernel<DIM, NT>;
@@ -890,8 +903,9 @@ static int clip_pairs_impl(const crg_options *opts, const crg_cells *dst, const 
     CRG_TRY(dstats.alloc_tmp(2, st));
     CRG_CUDA(cudaMemsetAsync(nflip.p, 0, 4 * sizeof(unsigned int), st));
     CRG_CUDA(cudaMemsetAsync(dstats.p, 0, 2 * sizeof(BPStats), st));
-    if (nd) { bp_bounds_kernel<DIM><<<ceil_div(nd, 256), 256, 0, st>>>(gd.view, gd.diam.p, dstats.p, 1e30f, 1.0, a_dst.p, gd.flip.p, nflip.p); CRG_LAUNCH_CHECK(); }
-    if (ns) { bp_bounds_kernel<DIM><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, gs.diam.p, dstats.p + 1, 1e30f, 1.0, a_src.p, gs.flip.p, nflip.p + 1); CRG_LAUNCH_CHECK(); }
+    const float big_chord = 1e30f;
+    if (nd) { bp_bounds_kernel<DIM><<<ceil_div(nd, 256), 256, 0, st>>>(gd.view, gd.diam.p, dstats.p, big_chord, 1.0, a_dst.p, gd.flip.p, nflip.p); CRG_LAUNCH_CHECK(); }
+    if (ns) { bp_bounds_kernel<DIM><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, gs.diam.p, dstats.p + 1, big_chord, 1.0, a_src.p, gs.flip.p, nflip.p + 1); CRG_LAUNCH_CHECK(); }
     gd.view.flip = gd.flip.p;
     gs.view.flip = gs.flip.p;
     DevBuf<int64_t> di, si;
@@ -1027,21 +1041,13 @@ static void destroy_handle(crg_regridder *R) {
     int prev = -1;
     cudaGetDevice(&prev);
     cudaSetDevice(R->device);
-    cudaStream_t st = R->own_stream;
-    // Everything is released (stream-ordered) on the library stream.  Work may still be in flight on a caller
-    // stream (crg_options.stream / crg_set_stream + crg_apply_async): the library stream first waits for it,
-    // so the pool cannot hand the matrix to another allocation while a kernel still reads it.
-    if (R->stream && R->stream != st) {
-        cudaEvent_t ev = nullptr;
-        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) {
-            if (cudaEventRecord(ev, R->stream) != cudaSuccess || cudaStreamWaitEvent(st, ev, 0) != cudaSuccess)
-                cudaStreamSynchronize(R->stream);
-            cudaEventDestroy(ev);
-        } else {
-            cudaStreamSynchronize(R->stream);
-        }
-        cudaGetLastError();
-    }
+    // Everything is released stream-ordered on the stream the handle WORKS on (crg_options.stream / crg_set_stream, else
+    // the library stream): work still in flight there (crg_apply_async) is ordered before the release, and the next
+    // build on the same stream gets the blocks back at once.  (Releasing on the library stream behind an event of the
+    // caller's stream was measured: the pool cannot hand such blocks to an allocation that the host enqueues before the
+    // event has completed, and a steady loop of builds paid ~1 ms per build for fresh driver allocations.)
+    // The caller's stream must therefore outlive the handle (include/crg_b200.h: crg_free).
+    cudaStream_t st = R->stream ? R->stream : R->own_stream;
     auto rebind = [&](auto &buf) { buf.s = st; buf.release(); };
     rebind(R->A.rowptr); rebind(R->A.colidx); rebind(R->A.vals);
     rebind(R->At.rowptr); rebind(R->At.colidx); rebind(R->At.vals);
@@ -1051,7 +1057,7 @@ static void destroy_handle(crg_regridder *R) {
     }
     rebind(R->dst_areas); rebind(R->src_areas); rebind(R->scratch_max); rebind(R->cand_pairs);
     rebind(R->stage_src); rebind(R->stage_dst);
-    delete R;   // buffers were released stream-ordered on the shared library stream; no sync needed
+    delete R;   // buffers were released stream-ordered; no sync needed
     if (prev >= 0) cudaSetDevice(prev);
     cudaGetLastError();
 }

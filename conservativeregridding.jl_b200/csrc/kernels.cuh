@@ -4,6 +4,7 @@
 #pragma once
 #include "common.cuh"
 #include "geom.cuh"
+#include "clipfast.cuh"
 #include "broadphase.cuh"
 
 namespace crg {
@@ -116,6 +117,199 @@ __global__ void __launch_bounds__(NT) clip_quad_kernel(CellsView gd, CellsView g
             }
             __syncwarp();
         }
+    }
+    nz = warp_sum(nz);
+    if (lane == 0 && nz) atomicAdd(&tile_count[base / CLIP_TILE], (uint32_t)nz);
+}
+
+// ---- spherical quadrilaterals: wedge sums (clipfast.cuh) for most pairs, symbolic Sutherland-Hodgman for the rest ------
+// Per cell of the CLIP grid, once: the edge-plane normals (exact products, orientation folded in) and the four corners
+// AS THE COMPUTED PLANES DEFINE THEM, corner j = normalise(n_{j-1} x n_j).  The cross product of two nearly parallel
+// unit vectors carries an absolute error of ~1e-16, i.e. the computed great circle misses its own end points by
+// ~1e-16 / (edge length); a polygon clipped against the computed planes (Sutherland-Hodgman) has its corner where the
+// planes meet, and the wedge sum of clipfast.cuh must use the same point P -- with the stored vertex instead, the two
+// differ by ~1e-16 * (polygon size / edge length), measured 2e-17 on config 5 (4e-12 of the largest entry).
+__global__ void __launch_bounds__(256) quad_normals_kernel(CellsView g, double *__restrict__ nrm, double *__restrict__ corners) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= g.ncells) return;
+    double v[4][3], n[4][3], p[4][3];
+    load_quad<3>(g.verts + c * 12, false, v);
+    cf_quad_normals(v, g.flip && g.flip[c], n);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const double *a = n[(j + 3) & 3], *b = n[j];
+        const double c0 = a[1] * b[2] - a[2] * b[1], c1 = a[2] * b[0] - a[0] * b[2], c2 = a[0] * b[1] - a[1] * b[0];
+        const double cc = c0 * c0 + c1 * c1 + c2 * c2;
+        const double na = a[0] * a[0] + a[1] * a[1] + a[2] * a[2], nb = b[0] * b[0] + b[1] * b[1] + b[2] * b[2];
+        if (cc > 1e-24 * na * nb && cc > 0.0) {              // the two planes meet at a usable angle
+            double inv = rsqrt(cc);
+            if (c0 * v[j][0] + c1 * v[j][1] + c2 * v[j][2] < 0.0) inv = -inv;
+            p[j][0] = c0 * inv; p[j][1] = c1 * inv; p[j][2] = c2 * inv;
+        } else {                                              // a zero-length edge (pole) or a straight angle: the vertex,
+            const double *m = na >= nb ? a : b;               // moved onto the plane of the longer edge
+            const double mm = na >= nb ? na : nb;
+            const double t = mm > 0.0 ? (m[0] * v[j][0] + m[1] * v[j][1] + m[2] * v[j][2]) / mm : 0.0;
+            p[j][0] = v[j][0] - t * m[0]; p[j][1] = v[j][1] - t * m[1]; p[j][2] = v[j][2] - t * m[2];
+        }
+    }
+    double2 *o = reinterpret_cast<double2 *>(nrm + c * 12), *q = reinterpret_cast<double2 *>(corners + c * 12);
+    const double *f = &n[0][0], *h = &p[0][0];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { o[i] = make_double2(f[2 * i], f[2 * i + 1]); q[i] = make_double2(h[2 * i], h[2 * i + 1]); }
+}
+
+// A warp owns CF_CHUNK consecutive candidate pairs and alternates between three stages, without block barriers:
+//   1. CLASSIFY, 32 pairs at a time, one lane per pair (cf_classify): empty -> area 0; inside -> the subject's own area;
+//      fast (one edge or two adjacent edges cut) -> queue F; general (three or four cutting edges, two opposite ones)
+//      -> queue G.  Queue entries carry the two cell ids, so the later stages do not go back to the pair list.
+//   2. WEDGE, whenever queue F holds 32 jobs (and for what is left at the end of the chunk): every lane takes one job
+//      and runs cf_wedge_area -- full warps of straight-line code, no shared-memory polygon, no divergence.
+//   3. GENERAL, whenever queue G holds 32 jobs: geom.cuh's symbolic Sutherland-Hodgman (quad_cut_area) on the warp's
+//      point table, which shares its shared memory with the record stage.
+// The 96-byte records with SCATTERED cell ids (source-side cells in stage 1, subject cells in stage 2) are fetched by
+// the whole warp -- six consecutive lanes read the six 16-byte pieces of one record, so a load instruction touches ~6
+// lines instead of 32 -- and handed to their lanes through a padded shared-memory stage (112-byte stride:
+// conflict-free 16-byte reads).  The destination side's records are the same for runs of consecutive pairs (the list
+// is grouped by destination cell) and are read directly.
+// The source cell is always the subject and the destination cell the clip cell, like the reference's
+// intersection_operator(src_polygon, dst_polygon) (intersection_areas.jl:21-23): with the roles swapped the result
+// differs by the round-off of the other clip order (measured up to 1.6e-16 on config 4, beyond the parity bar for
+// slivers), however much cheaper the swap would make grids whose source cells are the larger ones.
+#ifndef CF_MINB
+#define CF_MINB 5
+#endif
+constexpr int CF_NT = 128;
+constexpr int CF_REC = 112;
+constexpr int CF_CHUNK = 1024;      // = CLIP_TILE: one tile counter per warp
+static_assert(CF_CHUNK == CLIP_TILE, "one warp per compaction tile");
+constexpr int CF_WARP_SMEM = QUAD_SLOTS * 3 * 32 * 8;      // the warp's point table (stage 3); the record stage lives in it
+static_assert(CF_WARP_SMEM >= 32 * CF_REC, "the record stage fits into the point table");
+
+// the warp fetches the 96-byte records rec[id * 12 ..] of its 32 lanes' ids into the stage; every lane then reads its own
+__device__ __forceinline__ void cf_stage_records(const double *__restrict__ rec, int id, int lane, unsigned char *stage,
+                                                 double (&out)[4][3]) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const int c = k * 32 + lane, j = c / 6, part = c - 6 * j;
+        const int sj = __shfl_sync(CRG_FULL, id, j);
+        const double2 v = __ldg(reinterpret_cast<const double2 *>(rec + (int64_t)sj * 12) + part);
+        *reinterpret_cast<double2 *>(stage + j * CF_REC + part * 16) = v;
+    }
+    __syncwarp();
+    double *f = &out[0][0];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const double2 v = *reinterpret_cast<const double2 *>(stage + lane * CF_REC + k * 16);
+        f[2 * k] = v.x; f[2 * k + 1] = v.y;
+    }
+    __syncwarp();
+}
+
+struct CfJob { int subj, clp; uint32_t bits; };      // bits: 10 pair-in-chunk | 4 cutting edges / (2 first edge, 1 two, 1 none)
+
+__global__ void __launch_bounds__(CF_NT, CF_MINB)
+clip_quad_fast_kernel(CellsView gd, CellsView gs, const double *__restrict__ clip_nrm, const double *__restrict__ clip_corners,
+                      const int2 *__restrict__ pairs, int64_t npairs, double thresh,
+                      const double *__restrict__ unit_subj_areas, double *__restrict__ area_out,
+                      uint32_t *__restrict__ tile_count) {
+    extern __shared__ __align__(16) unsigned char cf_smem[];
+    __shared__ CfJob s_queue[CF_NT / 32][2][64];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t base = ((int64_t)blockIdx.x * (CF_NT / 32) + wid) * CF_CHUNK;
+    if (base >= npairs) return;
+    unsigned char *stage = cf_smem + wid * CF_WARP_SMEM;
+    CfJob (*queue)[64] = s_queue[wid];
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const double *__restrict__ subj_verts = gs.verts;
+    const uint8_t *__restrict__ subj_flip = gs.flip;
+    int qf = 0, qg = 0, nz = 0;                           // queue lengths (warp-uniform), surviving pairs of this lane
+#pragma unroll 1
+    for (int round = 0;; ++round) {
+        const bool more = round < CF_CHUNK / 32 && base + round * 32 < npairs;      // (warp-uniform)
+        if (more) {
+            // ---- stage 1: classify 32 pairs ---------------------------------------------------------------------
+            const int64_t idx = base + round * 32 + lane;
+            const bool live = idx < npairs;
+            const int2 pr = live ? pairs[idx] : make_int2(0, 0);
+            double s[4][3], n[4][3];
+            {
+                const double2 *yp = reinterpret_cast<const double2 *>(clip_nrm + (int64_t)pr.y * 12);      // read directly
+                double *yf = &n[0][0];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { const double2 v = __ldg(yp + k); yf[2 * k] = v.x; yf[2 * k + 1] = v.y; }
+                cf_stage_records(subj_verts, pr.x, lane, stage, s);
+            }
+            int e1;
+            bool two;
+            uint32_t cut;
+            int kind = cf_classify(s, n, e1, two, cut);
+            if (!live) kind = CF_EMPTY;
+            const int subj = pr.x, clp = pr.y;
+            const bool inside_wedge = kind == CF_INSIDE && !unit_subj_areas;      // (radius != 1: no unit areas at hand)
+            const bool pushf = kind == CF_FAST || inside_wedge, pushg = kind == CF_GENERAL;
+            if (live && !pushf && !pushg) {
+                double area = kind == CF_INSIDE ? unit_subj_areas[subj] : 0.0;
+                if (!(area > thresh) || !(area > 0.0)) area = 0.0;     // `area > 0` (intersection_areas.jl:24); NaN drops too
+                area_out[idx] = area;
+                nz += area != 0.0;
+            }
+            const unsigned fm = __ballot_sync(CRG_FULL, pushf), gm = __ballot_sync(CRG_FULL, pushg);
+            const uint32_t pic = (uint32_t)(round * 32 + lane);
+            if (pushf) queue[0][qf + __popc(fm & lt_mask)] = CfJob{subj, clp, pic | ((uint32_t)e1 << 10) | ((two ? 1u : 0u) << 12) | ((inside_wedge ? 1u : 0u) << 13)};
+            if (pushg) queue[1][qg + __popc(gm & lt_mask)] = CfJob{subj, clp, pic | (cut << 10)};
+            qf += __popc(fm); qg += __popc(gm);
+            __syncwarp();
+        }
+        // ---- stage 2: wedge sums, full warps -------------------------------------------------------------------------
+#pragma unroll 1
+        while (qf >= 32 || (!more && qf > 0)) {
+            const int take = min(qf, 32);
+            qf -= take;
+            const bool have = lane < take;
+            const CfJob job = queue[0][qf + (have ? lane : 0)];                  // (idle lanes shadow lane 0's job)
+            const int e1 = (job.bits >> 10) & 3, e2 = (e1 + 1) & 3;
+            const bool two = (job.bits >> 12) & 1u, none = (job.bits >> 13) & 1u;
+            const double *np1 = clip_nrm + (int64_t)job.clp * 12 + 3 * e1, *np2 = clip_nrm + (int64_t)job.clp * 12 + 3 * e2;
+            const double *pv = clip_corners + (int64_t)job.clp * 12 + 3 * e2;
+            const double n1[3] = {__ldg(np1), __ldg(np1 + 1), __ldg(np1 + 2)};
+            const double n2[3] = {__ldg(np2), __ldg(np2 + 1), __ldg(np2 + 2)};
+            const double P[3] = {__ldg(pv), __ldg(pv + 1), __ldg(pv + 2)};
+            const bool sflip = subj_flip && subj_flip[job.subj];
+            double s[4][3];
+            cf_stage_records(subj_verts, job.subj, lane, stage, s);
+            double d1[4], d2[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {      // the expressions of cf_classify: the same bits
+                const double a = fma(n1[0], s[i][0], fma(n1[1], s[i][1], n1[2] * s[i][2]));
+                const double b = fma(n2[0], s[i][0], fma(n2[1], s[i][1], n2[2] * s[i][2]));
+                d1[i] = none ? 1.0 : a;
+                d2[i] = two ? b : 1.0;
+            }
+            double area = cf_wedge_area(s, d1, d2, P);
+            if (sflip) area = -area;
+            if (!(area > thresh) || !(area > 0.0)) area = 0.0;
+            if (have) { area_out[base + (job.bits & 1023u)] = area; nz += area != 0.0; }
+        }
+        // ---- stage 3: the general pairs, symbolic Sutherland-Hodgman on the warp's point table -----------------------------
+#pragma unroll 1
+        while (qg >= 32 || (!more && qg > 0)) {
+            const int take = min(qg, 32);
+            qg -= take;
+            const bool have = lane < take;
+            const CfJob job = queue[1][qg + (have ? lane : 0)];
+            __syncwarp();
+            double area = 0.0;
+            if (have) {
+                // (quad_cut_area addresses its table as smem[(id * 3 + c) * 32 + threadIdx.x]: hand it the warp's block)
+                double *table = reinterpret_cast<double *>(stage) - (threadIdx.x - lane);
+                area = quad_cut_area<3, 32>(gs, job.subj, gd, job.clp, (job.bits >> 10) & 15u, table);
+                if (!(area > thresh) || !(area > 0.0)) area = 0.0;
+                area_out[base + (job.bits & 1023u)] = area;
+                nz += area != 0.0;
+            }
+            __syncwarp();
+        }
+        if (!more) break;
     }
     nz = warp_sum(nz);
     if (lane == 0 && nz) atomicAdd(&tile_count[base / CLIP_TILE], (uint32_t)nz);

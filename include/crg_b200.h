@@ -167,6 +167,8 @@ int crg_build_from_coo(const crg_options *opts, int64_t n_dst, int64_t n_src, in
 int crg_clip_pairs(const crg_options *opts, const crg_cells *dst, const crg_cells *src, int64_t n_pairs,
                    const int64_t *src_idx, const int64_t *dst_idx, double *area_out);
 
+/* Releases the handle's device memory, stream-ordered on the stream the handle works on (crg_options.stream /
+ * crg_set_stream, else the library's): a caller-provided stream must still exist when crg_free is called. */
 int crg_free(crg_regridder *r);
 
 int crg_dims(const crg_regridder *r, int64_t *n_dst, int64_t *n_src, int64_t *nnz);
