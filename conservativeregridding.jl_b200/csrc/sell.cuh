@@ -216,80 +216,88 @@ __global__ void __launch_bounds__(256) spmv_sell_kernel(SellView S, const double
 }
 
 
-// Persistent, software-pipelined variant: a warp walks slices s, s + W, s + 2W, ... and always has the
-// NEXT slice's header (offset, row length, permutation, area) and first SELL_UNR steps of (col, val) in
-// flight while it gathers x for the current one, so a slice costs about one memory latency instead of
-// three dependent ones.  Pays off when slices are short (transpose direction: ~3 entries per row).
+// Persistent, software-pipelined variant for matrices whose slices are short (the transpose direction: ~3 entries per
+// row): a warp walks slices w, w + W, w + 2W, ... three deep -- while slice s is summed, the gathers of x for slice
+// s + W, the first SELL_UNR steps of (col, val) + the area of slice s + 2W and the header (offset, row length,
+// permutation) of slice s + 3W are in flight, and everything a slice consumes was requested at least one iteration
+// earlier: no load of an iteration depends on another load of the same iteration.  cfg5 transpose on B200: one warp per
+// slice 62 us -> two-deep pipeline (next header + first steps in flight; still ~3 serialised latencies per slice)
+// 56 us -> three deep 45 us (62 % of measured HBM).  Measured and dropped: a contiguous run of slices per warp
+// instead of the stride W (80-200 us: the warps of a wave then hit far fewer DRAM pages at a time), 128-thread
+// blocks (45-61 us, no better), 64 registers for 4 blocks per SM (spills: 78-98 us).  The grid size matters more than
+// expected (8 blocks per SM in the grid, 3 resident: 45 us; 6: 51; 16: 49; 48: 63).
 template <bool DIVIDE>
-__global__ void __launch_bounds__(256) spmv_sell_pipelined_kernel(SellView S, const double *__restrict__ x,
-                                                                  double *__restrict__ y,
-                                                                  const double *__restrict__ areas) {
+__global__ void __launch_bounds__(256, 3) spmv_sell_pipelined_kernel(SellView S, const double *__restrict__ x,
+                                                                      double *__restrict__ y,
+                                                                      const double *__restrict__ areas) {
     const int lane = threadIdx.x & 31;
     const int W = gridDim.x * (blockDim.x >> 5);
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int step = W;
+    const int n = S.nslices;
     struct Hdr { int off, steps, len, r; };
     auto load_hdr = [&](int s) {
-        Hdr h;
-        h.off = __ldg(&S.slice_off[s]);
-        h.steps = __ldg(&S.slice_off[s + 1]) - h.off;
-        h.len = __ldg(&S.rlen[(int64_t)s * 32 + lane]);
-        h.r = __ldg(&S.perm[(int64_t)s * 32 + lane]);
+        Hdr h{0, 0, 0, -1};
+        if (s < n) {
+            h.off = __ldg(&S.slice_off[s]);
+            h.steps = __ldg(&S.slice_off[s + 1]) - h.off;
+            h.len = __ldg(&S.rlen[(int64_t)s * 32 + lane]);
+            h.r = __ldg(&S.perm[(int64_t)s * 32 + lane]);
+        }
         return h;
     };
-    int c[SELL_UNR], cn[SELL_UNR];
-    double v[SELL_UNR], vn[SELL_UNR];
-    auto load_round = [&](const Hdr &h, int j, int (&cc)[SELL_UNR], double (&vv)[SELL_UNR]) {
-        const size_t e = ((size_t)h.off + j) * 32 + lane;
+    auto load_round = [&](const Hdr &h, int (&cc)[SELL_UNR], double (&vv)[SELL_UNR], double &ar) {
+        const size_t e = (size_t)h.off * 32 + lane;
         const int jend = min(h.len, SELL_HP);
 #pragma unroll
         for (int u = 0; u < SELL_UNR; ++u) {
-            const bool ok = j + u < jend;
+            const bool ok = u < jend;
             cc[u] = ok ? SELL_LD(S.cols + e + (size_t)u * 32) : 0;
             vv[u] = ok ? SELL_LD(S.vals + e + (size_t)u * 32) : 0.0;
         }
+        ar = (DIVIDE && h.r >= 0) ? __ldg(&areas[h.r]) : 1.0;
+    };
+    auto gather = [&](const Hdr &h, const int (&cc)[SELL_UNR], double (&xx)[SELL_UNR]) {
+        const int jend = min(h.len, SELL_HP);
+#pragma unroll
+        for (int u = 0; u < SELL_UNR; ++u) xx[u] = (u < jend) ? __ldg(&x[cc[u]]) : 0.0;
     };
     int s = w;
-    Hdr h{0, 0, 0, -1}, hn{0, 0, 0, -1};
-    double area = 1.0, arean = 1.0;
-    if (s < S.nslices) {
-        h = load_hdr(s);
-        load_round(h, 0, c, v);
-        if (DIVIDE && h.r >= 0) area = __ldg(&areas[h.r]);
+    Hdr h0 = load_hdr(s), h1 = load_hdr(s + step), h2 = load_hdr(s + 2 * step);
+    int c1[SELL_UNR], c2[SELL_UNR];
+    double v0[SELL_UNR], v1[SELL_UNR], v2[SELL_UNR], x0[SELL_UNR], x1[SELL_UNR];
+    double a0 = 1.0, a1 = 1.0, a2 = 1.0;
+    {
+        int c0[SELL_UNR];
+        load_round(h0, c0, v0, a0);
+        load_round(h1, c1, v1, a1);
+        gather(h0, c0, x0);
     }
-    while (s < S.nslices) {
-        const int sn = s + W;
-        if (sn < S.nslices) hn = load_hdr(sn);
-        // ---- current slice, round 0 is already in registers -------------------------------------------
-        const int jend = min(h.len, SELL_HP), wend = min(h.steps, SELL_HP);
+    while (s < n) {
+        const Hdr h3 = load_hdr(s + 3 * step);                    // three ahead: header
+        load_round(h2, c2, v2, a2);                            // two ahead: first steps + area (its header arrived an iteration ago)
+        gather(h1, c1, x1);                                    // one ahead: gathers (its column indices arrived an iteration ago)
+        // ---- current slice --------------------------------------------------------------------------------------
+        const int jend = min(h0.len, SELL_HP), wend = min(h0.steps, SELL_HP);
         double acc = 0.0;
-        {
-            double xv[SELL_UNR];
 #pragma unroll
-            for (int u = 0; u < SELL_UNR; ++u) xv[u] = (u < jend) ? __ldg(&x[c[u]]) : 0.0;
-            // the next slice's first round goes out before we wait for the gathers
-            if (sn < S.nslices) {
-                load_round(hn, 0, cn, vn);
-                if (DIVIDE && hn.r >= 0) arean = __ldg(&areas[hn.r]);
-            }
+        for (int u = 0; u < SELL_UNR; ++u) if (u < jend) acc += v0[u] * x0[u];
+        for (int j = SELL_UNR; j < wend; j += SELL_UNR) {      // taller slices: remaining steps, loaded here
+            const size_t e = ((size_t)h0.off + j) * 32 + lane;
 #pragma unroll
-            for (int u = 0; u < SELL_UNR; ++u) if (u < jend) acc += v[u] * xv[u];
+            for (int u = 0; u < SELL_UNR; ++u)
+                if (j + u < jend) acc += SELL_LD(S.vals + e + (size_t)u * 32) * __ldg(&x[SELL_LD(S.cols + e + (size_t)u * 32)]);
         }
-        for (int j = SELL_UNR; j < wend; j += SELL_UNR) {      // taller slices: remaining rounds
-            int c2[SELL_UNR];
-            double v2[SELL_UNR];
-            load_round(h, j, c2, v2);
-#pragma unroll
-            for (int u = 0; u < SELL_UNR; ++u) if (j + u < jend) acc += v2[u] * __ldg(&x[c2[u]]);
-        }
-        if (h.steps <= SELL_HP) {
-            if (h.r >= 0) y[h.r] = DIVIDE ? acc / area : acc;
+        if (h0.steps <= SELL_HP) {
+            if (h0.r >= 0) y[h0.r] = DIVIDE ? acc / a0 : acc;
         } else {                                               // piece 0 of a cut slice
-            sell_finish_cut<DIVIDE>(S, (int)__ldg(&S.cut_base[s]), 0, (h.steps + SELL_HP - 1) / SELL_HP, lane, h.r, acc,
-                                    area, y);
+            sell_finish_cut<DIVIDE>(S, (int)__ldg(&S.cut_base[s]), 0, (h0.steps + SELL_HP - 1) / SELL_HP, lane, h0.r, acc, a0, y);
         }
-        h = hn; area = arean; s = sn;
+        s += step;
+        h0 = h1; h1 = h2; h2 = h3;
+        a0 = a1; a1 = a2;
 #pragma unroll
-        for (int u = 0; u < SELL_UNR; ++u) { c[u] = cn[u]; v[u] = vn[u]; }
+        for (int u = 0; u < SELL_UNR; ++u) { v0[u] = v1[u]; x0[u] = x1[u]; c1[u] = c2[u]; v1[u] = v2[u]; }
     }
     // ---- extra pieces of cut slices (rare) -----------------------------------------------------------------
     for (int p = w; p < S.npieces; p += W) {

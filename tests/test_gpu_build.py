@@ -12,6 +12,7 @@ from helpers import (GOLDEN, GRID_PAIRS_SMALL, KAT_DST_AREAS, KAT_MATRIX, KAT_SR
                      kat_simple)
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _oracle():
@@ -572,3 +573,33 @@ def test_tripolar_fold_row_ghost_cells_and_mirroring(gpu):
         back = np.zeros(other.ncells); regrid_(back, transpose(R), y)
         onto = np.zeros(tri.ncells); regrid_(onto, transpose(RT), yo)
         assert np.array_equal(onto[base + partner], onto[base + real])
+
+
+def test_wedge_clip_variant_against_the_shipped_kernel(gpu, tmp_path):
+    """CRG_CLIP_FAST=1 routes spherical quadrilaterals through the wedge-sum path (csrc/clipfast.cuh; measured, not the
+    default -- profiles/README.md): same matrices within the parity bar, same areas, on a HEALPix -> lon-lat pair, a
+    nested lon-lat pair (coincident edges) and a pair whose source cells are the larger ones (mostly general pairs)."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np, scipy.sparse as sp
+sys.path.insert(0, %r)
+from crg_b200 import grids
+from crg_b200.regridder import Regridder
+pairs = [(grids.lonlat_grid(180, 90), grids.healpix_grid(64, "ring")), (grids.lonlat_grid(90, 45), grids.lonlat_grid(180, 90)),
+         (grids.healpix_grid(32, "nested"), grids.lonlat_grid(90, 45))]
+for k, (d, s) in enumerate(pairs):
+    R = Regridder(d, s)
+    sp.save_npz(sys.argv[1] + "_%%d.npz" %% k, R.intersections.tocsc())
+    np.save(sys.argv[1] + "_%%d_areas.npy" %% k, np.concatenate([R.dst_areas, R.src_areas]))
+''' % ROOT
+    out = {}
+    for mode in ("0", "1"):
+        env = dict(os.environ, CRG_CLIP_FAST=mode)
+        subprocess.run([sys.executable, "-c", code, str(tmp_path / ("m" + mode))], check=True, env=env)
+        out[mode] = [(sp.load_npz(str(tmp_path / f"m{mode}_{k}.npz")), np.load(str(tmp_path / f"m{mode}_{k}_areas.npy"))) for k in range(3)]
+    for (A0, a0), (A1, a1) in zip(out["0"], out["1"]):
+        assert np.array_equal(a0, a1)
+        nd = A0.shape[0]
+        compare_matrices(A1, A0, a0[:nd], a0[nd:])
+        assert abs(A1.sum() - A0.sum()) <= 1e-13 * A0.sum()
