@@ -6,10 +6,13 @@ from crg_b200 import grids
 from crg_b200.regridder import Regridder, regrid_, transpose
 K = int(os.environ.get("K", "100"))
 st = torch.cuda.Stream(); torch.cuda.set_stream(st)
-R = Regridder(grids.lonlat_spec(360, 180), grids.cubed_sphere_spec(180), stream=st.cuda_stream)
+PAIR = os.environ.get("PAIR", "cfg3")
+R = (Regridder(grids.lonlat_spec(360, 180), grids.cubed_sphere_spec(180), stream=st.cuda_stream) if PAIR == "cfg3" else
+     Regridder(grids.lonlat_spec(360, 180), grids.healpix_spec(128, "ring"), stream=st.cuda_stream) if PAIR == "healpix" else
+     Regridder(grids.lonlat_spec(360, 180), grids.lonlat_spec(720, 360), stream=st.cuda_stream))
 n_dst, n_src = R.shape
 nnz = R.intersections.nnz
-print("cfg3 n_dst", n_dst, "n_src", n_src, "nnz", nnz, "build ms", R.intersections.stats()["ms_device"])
+print(PAIR, "n_dst", n_dst, "n_src", n_src, "nnz", nnz, "build ms", R.intersections.stats()["ms_device"])
 flush = torch.zeros(64 << 20, dtype=torch.float32, device="cuda")
 by = R.intersections.apply_bytes(K, True)
 for name, mk in (("level-fastest (cells,K) C-order", lambda n: torch.rand(n, K, dtype=torch.float64, device="cuda")),
