@@ -230,7 +230,8 @@ __device__ __forceinline__ bool ring_is_convex(const double *p, int n, bool cloc
 template <int DIM>
 __global__ void __launch_bounds__(256) bp_bounds_kernel(CellsView g, float *__restrict__ diam, BPStats *st,
                                                         float big_chord, double scale, double *__restrict__ areas,
-                                                        uint8_t *__restrict__ flip, unsigned int *__restrict__ nflip) {
+                                                        uint8_t *__restrict__ flip, unsigned int *__restrict__ nflip,
+                                                        double *__restrict__ normals = nullptr) {
     __shared__ CellStage<DIM> stage;
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     // bounding box of the vertices: exact (double) in the plane, where it becomes the bin-grid domain;
@@ -251,6 +252,20 @@ __global__ void __launch_bounds__(256) bp_bounds_kernel(CellsView g, float *__re
         const float d = cell_diameter<DIM>(p, n);
         diam[c] = d;
         if (!ring_is_convex<DIM>(p, n, f, (double)d)) atomicAdd(nflip + 2, 1u);   // nflip[2..3]: non-convex cells
+        if (DIM == 3 && normals && n == 4) {
+            // Edge-plane normals of a spherical quadrilateral for the clip kernel (the grid that clips: 12 doubles per cell,
+            // negated for a clockwise cell so that "inside" is n . x >= 0): the same edge_normal the clip would evaluate per
+            // candidate pair -- 36 FP64 operations per pair there, once per cell here (the convexity test needs them anyway).
+            double nn[12];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                edge_normal(p + 3 * e, p + 3 * ((e + 1) & 3), nn[3 * e], nn[3 * e + 1], nn[3 * e + 2]);
+                if (f) { nn[3 * e] = -nn[3 * e]; nn[3 * e + 1] = -nn[3 * e + 1]; nn[3 * e + 2] = -nn[3 * e + 2]; }
+            }
+            double2 *o = reinterpret_cast<double2 *>(normals + c * 12);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) o[i] = make_double2(nn[2 * i], nn[2 * i + 1]);
+        }
         if (DIM == 2 || d < big_chord) {
             sum = d; mx = d; cnt = 1;
             for (int i = 0; i < n; ++i)

@@ -561,7 +561,7 @@ static int device_side_stream(int dev, cudaStream_t *out);
 template <int DIM>
 static int launch_clip(const CellsView &gdv, const CellsView &gsv, bool fixed, int nv_dst, int nv_src, const int2 *pairs,
                        int64_t n_cand, double thresh, const double *unit_src_areas, double *pair_area,
-                       uint32_t *tile_count, cudaStream_t st) {
+                       uint32_t *tile_count, cudaStream_t st, const double *clip_nrm = nullptr) {
     static const bool allow_quad = !(getenv("CRG_CLIP_QUAD") && atoi(getenv("CRG_CLIP_QUAD")) == 0);
     const bool fixed4 = fixed && nv_dst <= 4 && nv_src <= 4;
     const bool quad = allow_quad && fixed4 && nv_dst == 4 && nv_src == 4 && ((uintptr_t)gdv.verts % 16 == 0) &&
@@ -589,11 +589,15 @@ static int launch_clip(const CellsView &gdv, const CellsView &gsv, bool fixed, i
     } else if (quad) {
         constexpr int NT = 128;
         const size_t smem = sizeof(double) * QUAD_SLOTS * DIM * NT;
-        auto kern = clip_quad_kernel<DIM, NT>;
+        // 256-bit vertex loads when every cell record is 32-byte aligned (spherical quadrilaterals are 96 bytes)
+        static const bool allow_wide = !(getenv("CRG_CLIP_WIDE") && atoi(getenv("CRG_CLIP_WIDE")) == 0);
+        const double *nrm = ((uintptr_t)clip_nrm % 32 == 0) ? clip_nrm : nullptr;
+        const bool wide = allow_wide && DIM == 3 && (uintptr_t)gdv.verts % 32 == 0 && (uintptr_t)gsv.verts % 32 == 0;
+        auto kern = wide ? clip_quad_kernel<DIM, NT, true> : clip_quad_kernel<DIM, NT, false>;
         CRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // an untouched source cell contributes its own area: reuse K4's (only when they are unit-sphere areas)
         kern<<<ceil_div(ceil_div(n_cand, CLIP_CHUNK), NT / 32), NT, smem, st>>>(gdv, gsv, pairs, n_cand, thresh,
-                                                                                unit_src_areas, pair_area, tile_count);
+                                                                                unit_src_areas, pair_area, tile_count, nrm);
     } else if (fixed4) CRG_CLIP(128, 8);
     else CRG_CLIP(64, 2 * CRG_MAX_VERTS);
 #undef CRG_CLIP
@@ -640,7 +644,12 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     CRG_CUDA(cudaMemcpyAsync(dstats.p, hst, sizeof(hst), cudaMemcpyHostToDevice, st));
     const double big_chord = 2.0 * std::sin(BP_BIG_ANGLE / 2.0);
     // (the views' flip pointers are still null here: the kernel sees the cells as stored)
-    if (nd) { bp_bounds_kernel<DIM><<<ceil_div(nd, 256), 256, 0, st>>>(gd.view, gd.diam.p, dstats.p, (float)big_chord, r2, R->dst_areas.p, gd.flip.p, nflip.p); CRG_LAUNCH_CHECK(); }
+    // spherical quadrilaterals: the destination (clip) grid's edge-plane normals come out of the same pass
+    DevBuf<double> dst_nrm;
+    static const bool allow_nrm = !(getenv("CRG_CLIP_NORMALS") && atoi(getenv("CRG_CLIP_NORMALS")) == 0);
+    if (allow_nrm && DIM == 3 && nd && !dst->offsets && !src->offsets && dst->nv == 4 && src->nv == 4)
+        CRG_TRY(dst_nrm.alloc_tmp((size_t)nd * 12, st));
+    if (nd) { bp_bounds_kernel<DIM><<<ceil_div(nd, 256), 256, 0, st>>>(gd.view, gd.diam.p, dstats.p, (float)big_chord, r2, R->dst_areas.p, gd.flip.p, nflip.p, dst_nrm.p); CRG_LAUNCH_CHECK(); }
     if (ns) { bp_bounds_kernel<DIM><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, gs.diam.p, dstats.p + 1, (float)big_chord, r2, R->src_areas.p, gs.flip.p, nflip.p + 1); CRG_LAUNCH_CHECK(); }
     gd.view.flip = gd.flip.p;
     gs.view.flip = gs.flip.p;
@@ -833,7 +842,7 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
         CRG_CUDA(cudaMemsetAsync(tile_count.p, 0, sizeof(uint32_t) * ((size_t)ntiles + 1), st));
         CRG_TRY((launch_clip<DIM>(gd.view, gs.view, !dst->offsets && !src->offsets, dst->nv, src->nv, pairs.p, n_cand,
                                   R->opts.area_threshold, r2 == 1.0 ? R->src_areas.p : nullptr, pair_area.p,
-                                  tile_count.p, st)));
+                                  tile_count.p, st, dst_nrm.p)));
         CRG_TRY((exclusive_scan<uint32_t, uint32_t>(tile_count.p, ntiles, tile_count.p, st)));
         CRG_CUDA(cudaMemcpyAsync(&h_keep, tile_count.p + ntiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CRG_CUDA(cudaStreamSynchronize(st));

@@ -238,6 +238,21 @@ __device__ double clip_pair_area(const CellsView &gs, int64_t s, const CellsView
 // Fast path: quadrilateral x quadrilateral (every structured grid of BASELINE.json): quad_prepass +
 // quad_cut_area below, driven by clip_quad_kernel (kernels.cuh).  Cells are fetched with 16-byte loads.
 // ------------------------------------------------------------------------------------
+// 256-bit loads (sm_100: LDG.256, three per spherical quadrilateral instead of six 128-bit ones -- a gather at a 96-byte
+// stride costs one L1 wavefront per lane and instruction, and the L1 data pipe is the clip kernel's busiest unit);
+// p must be 32-byte aligned.
+__device__ __forceinline__ void load_quad_wide(const double *__restrict__ p, double (&v)[4][3]) {
+    double t[12];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(t[4 * i]), "=d"(t[4 * i + 1]), "=d"(t[4 * i + 2]), "=d"(t[4 * i + 3]) : "l"(p + 4 * i));
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v[i][k] = t[i * 3 + k];
+}
+
 template <int DIM>
 __device__ __forceinline__ void load_quad(const double *__restrict__ p, bool flip, double (&v)[4][DIM]) {
     const double2 *q = reinterpret_cast<const double2 *>(p);
@@ -309,22 +324,32 @@ __device__ __forceinline__ int crossing_kind(double dp, double dq, bool p_inside
 // four subject corners inside can never cut (the working polygon only shrinks); one that leaves all
 // four outside empties the intersection (most false candidates end here).
 // Returns -1 (empty) or the 4-bit set of clip edges that cut.
-template <int DIM>
-__device__ __forceinline__ int quad_prepass(const CellsView &gs, int64_t s, const CellsView &gc, int64_t c) {
+// clip_nrm (sphere only, may be null): the clip grid's edge-plane normals, 12 doubles per cell, orientation folded in
+// (bp_bounds_kernel writes them with the same edge_normal, so the distances are the same bits either way).
+template <int DIM, bool WIDE = false>
+__device__ __forceinline__ int quad_prepass(const CellsView &gs, int64_t s, const CellsView &gc, int64_t c,
+                                            const double *__restrict__ clip_nrm = nullptr) {
     // Cells stored clockwise are NOT reversed: a clockwise clip cell has its interior on the other side
     // of every edge (the signed distances change sign); a clockwise subject only changes the sign of the
     // final area.
     double sv[4][DIM], cv[4][DIM];
-    load_quad<DIM>(gs.verts + s * 4 * DIM, false, sv);
-    load_quad<DIM>(gc.verts + c * 4 * DIM, false, cv);
-    const bool cflip = gc.flip && gc.flip[c];
+    const bool have_n = DIM == 3 && clip_nrm;
+    if constexpr (WIDE && DIM == 3) {
+        load_quad_wide(gs.verts + s * 12, sv);
+        load_quad_wide(have_n ? clip_nrm + c * 12 : gc.verts + c * 12, cv);
+    } else {
+        load_quad<DIM>(gs.verts + s * 4 * DIM, false, sv);
+        load_quad<DIM>(have_n ? clip_nrm + c * 4 * DIM : gc.verts + c * 4 * DIM, false, cv);
+    }
+    const bool cflip = !have_n && gc.flip && gc.flip[c];
     uint32_t cut = 0;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const double *u = cv[e], *v = cv[(e + 1) & 3];
         double nx, ny, nz = 0.0, h0 = 0.0;
         if (DIM == 3) {
-            edge_normal(u, v, nx, ny, nz);
+            if (have_n) { nx = u[0]; ny = u[1]; nz = u[2]; }
+            else edge_normal(u, v, nx, ny, nz);
         } else {
             nx = -(v[1] - u[1]); ny = v[0] - u[0];
             h0 = -(nx * u[0] + ny * u[1]);
@@ -345,16 +370,18 @@ __device__ __forceinline__ int quad_prepass(const CellsView &gs, int64_t s, cons
 
 // Area of subject ∩ clip given the set of cutting clip edges (quad_prepass).  A lane only visits ITS
 // cutting edges, so the lanes of a warp meet in the cut code even when different edges cut them.
-template <int DIM, int NT>
+template <int DIM, int NT, bool WIDE = false>
 __device__ double quad_cut_area(const CellsView &gs, int64_t s, const CellsView &gc, int64_t c, uint32_t cut,
-                                double *smem /* QUAD_SLOTS * DIM * NT doubles */) {
+                                double *smem /* QUAD_SLOTS * DIM * NT doubles */, const double *__restrict__ clip_nrm = nullptr) {
     PointTable<DIM, NT> tab{smem + threadIdx.x};
-    const double *cbase = gc.verts + c * 4 * DIM;
-    const double sc = (gc.flip && gc.flip[c]) ? -1.0 : 1.0;        // clockwise clip cell: normals negated
+    const bool have_n = DIM == 3 && clip_nrm;
+    const double *cbase = have_n ? clip_nrm + c * 4 * DIM : gc.verts + c * 4 * DIM;
+    const double sc = (!have_n && gc.flip && gc.flip[c]) ? -1.0 : 1.0;        // clockwise clip cell: normals negated
     const double ss = (gs.flip && gs.flip[s]) ? -1.0 : 1.0;        // clockwise subject: area negated
     {
         double sv[4][DIM];
-        load_quad<DIM>(gs.verts + s * 4 * DIM, false, sv);
+        if constexpr (WIDE && DIM == 3) load_quad_wide(gs.verts + s * 12, sv);
+        else load_quad<DIM>(gs.verts + s * 4 * DIM, false, sv);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -368,11 +395,14 @@ __device__ double quad_cut_area(const CellsView &gs, int64_t s, const CellsView 
         const int iu = e, iv = (e + 1) & 3;
         double u[3] = {0.0, 0.0, 0.0}, v[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-        for (int k = 0; k < DIM; ++k) { u[k] = __ldg(cbase + iu * DIM + k); v[k] = __ldg(cbase + iv * DIM + k); }
+        for (int k = 0; k < DIM; ++k) { u[k] = __ldg(cbase + iu * DIM + k); if (!have_n) v[k] = __ldg(cbase + iv * DIM + k); }
         double nx, ny, nz = 0.0, h0 = 0.0;
         if (DIM == 3) {
-            edge_normal(u, v, nx, ny, nz);
-            nx *= sc; ny *= sc; nz *= sc;
+            if (have_n) { nx = u[0]; ny = u[1]; nz = u[2]; }
+            else {
+                edge_normal(u, v, nx, ny, nz);
+                nx *= sc; ny *= sc; nz *= sc;
+            }
         } else {
             nx = -sc * (v[1] - u[1]); ny = sc * (v[0] - u[0]);
             h0 = -(nx * u[0] + ny * u[1]);

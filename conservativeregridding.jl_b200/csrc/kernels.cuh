@@ -56,11 +56,14 @@ __global__ void __launch_bounds__(NT) clip_kernel(CellsView gd, CellsView gs, co
 // Every pair's area is written exactly once; the non-zero count goes to the tile counter at the end.
 constexpr int CLIP_CHUNK = 512;     // divides CLIP_TILE
 constexpr int CLIP_QUEUES = 2;
-template <int DIM, int NT>
+// clip_nrm: the destination grid's edge-plane normals from the bounds pass (sphere; null: computed per pair).  WIDE: 256-bit
+// vertex loads (every cell record 32-byte aligned).
+template <int DIM, int NT, bool WIDE = false>
 __global__ void __launch_bounds__(NT) clip_quad_kernel(CellsView gd, CellsView gs, const int2 *__restrict__ pairs,
                                                        int64_t npairs, double thresh,
                                                        const double *__restrict__ unit_src_areas,
-                                                       double *__restrict__ area_out, uint32_t *__restrict__ tile_count) {
+                                                       double *__restrict__ area_out, uint32_t *__restrict__ tile_count,
+                                                       const double *__restrict__ clip_nrm = nullptr) {
     extern __shared__ double clip_smem[];
     __shared__ uint16_t s_queue[NT / 32][CLIP_QUEUES][64];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(NT) clip_quad_kernel(CellsView gd, CellsView g
         int state = -1;
         if (!last && idx < npairs) {
             const int2 pr = pairs[idx];
-            state = quad_prepass<DIM>(gs, pr.x, gd, pr.y);
+            state = quad_prepass<DIM, WIDE>(gs, pr.x, gd, pr.y, clip_nrm);
             double area = 0.0;
             if (state == 0 && unit_src_areas) { area = unit_src_areas[pr.x]; state = -1; }
             if (state < 0) {
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(NT) clip_quad_kernel(CellsView gd, CellsView g
             if (have) {
                 const int64_t jdx = base + (j & 511u);
                 const int2 pr = pairs[jdx];
-                double area = quad_cut_area<DIM, NT>(gs, pr.x, gd, pr.y, j >> 9, clip_smem);
+                double area = quad_cut_area<DIM, NT, WIDE>(gs, pr.x, gd, pr.y, j >> 9, clip_smem, clip_nrm);
                 if (!(area > thresh) || !(area > 0.0)) area = 0.0;     // `area > 0` (intersection_areas.jl:24); NaN drops too
                 area_out[jdx] = area;
                 nz += area != 0.0;
