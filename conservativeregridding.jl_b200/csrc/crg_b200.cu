@@ -748,8 +748,11 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     CRG_TRY(big_dst.alloc_tmp((size_t)nd, st));
     CRG_CUDA(cudaMemsetAsync(bin_count.p, 0, sizeof(uint32_t) * (nbins + 1), st));
     CRG_CUDA(cudaMemsetAsync(counters.p, 0, sizeof(uint32_t) * 4, st));
+    DevBuf<int4> bin_rec;                     // the count pass' box records, consumed by the fill pass
+    static const bool allow_rec = !(getenv("CRG_BIN_RECORDS") && atoi(getenv("CRG_BIN_RECORDS")) == 0);
+    if (allow_rec && ns) CRG_TRY(bin_rec.alloc_tmp((size_t)ns, st));
     if (ns) bp_bin_kernel<DIM, false><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, gs.diam.p, P, bin_count.p, nullptr,
-                                                                          nullptr, big_src.p, counters.p);
+                                                                          nullptr, big_src.p, counters.p, bin_rec.p);
     if (ns) CRG_LAUNCH_CHECK();
     CRG_TRY((exclusive_scan<uint32_t, uint32_t>(bin_count.p, (int64_t)nbins, bin_start.p, st)));
     uint32_t h_entries = 0, h_counters[4] = {0, 0, 0, 0};
@@ -762,8 +765,9 @@ static int build_impl(crg_regridder *R, const crg_cells *dst, const crg_cells *s
     DevBuf<int4> entries;
     CRG_TRY(entries.alloc_tmp((size_t)h_entries, st));
     CRG_CUDA(cudaMemsetAsync(bin_count.p, 0, sizeof(uint32_t) * (nbins + 1), st));
-    if (ns) bp_bin_kernel<DIM, true><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, gs.diam.p, P, bin_count.p, bin_start.p,
-                                                                         entries.p, nullptr, nullptr);
+    if (ns && bin_rec.p) bp_bin_fill_kernel<DIM><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, P, bin_rec.p, bin_count.p, bin_start.p, entries.p);
+    else if (ns) bp_bin_kernel<DIM, true><<<ceil_div(ns, 256), 256, 0, st>>>(gs.view, gs.diam.p, P, bin_count.p, bin_start.p,
+                                                                              entries.p, nullptr, nullptr);
     if (ns) CRG_LAUNCH_CHECK();
     CRG_TRY(tm.mark());   // 3
 
