@@ -13,4 +13,4 @@ timeout 500 ncu --set full --clock-control none --import-source on -k regex:"cli
 timeout 500 ncu --set full --clock-control none --import-source on -k regex:"spmv_sell" -c 2 -o gpurun_out/spmv_final -f python scripts/prof_build.py > gpurun_out/ncu_spmv.log 2>&1
 timeout 500 ncu --set full --clock-control none -k regex:"rs_downsweep_kernel|row_sort_split_kernel|sell_fill_kernel|bp_bounds_kernel|bp_bin_kernel|bp_query_kernel" -s 11 -c 11 -o gpurun_out/build_final -f python scripts/prof_build.py > gpurun_out/ncu_asm.log 2>&1
 ls -la gpurun_out/*.ncu-rep
-tail -3 gpurun_out/configs.txt gpurun_out/spmm.txt gpurun_out/apply.txt
+tail -n 3 gpurun_out/configs.txt; tail -n 3 gpurun_out/spmm.txt; tail -n 3 gpurun_out/apply.txt
