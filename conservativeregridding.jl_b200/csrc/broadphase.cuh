@@ -356,14 +356,16 @@ __global__ void __launch_bounds__(256) bp_bin_kernel(CellsView g, const float *_
             return;
     }
     unsigned faces = 0;          // faces that see the cell
-    if (!big) {     // total number of bins the cell would be inserted in (the boxes of the one or two faces
-        int cover = 0;  // that see it are recomputed below: cheaper than keeping them in local memory)
+    QBox b1;                     // the box on the (last) face that sees it: kept when it is the only one
+    if (!big) {     // total number of bins the cell would be inserted in (with two or three faces the boxes
+        int cover = 0;  // are recomputed below: cheaper than keeping them in local memory)
         for (int f = 0; f < P.nfaces; ++f) {
             QBox b;
             bool cl;
             if (cell_face_qbox<DIM>(p, n, f, P, &b, &cl)) {
                 cover += ((b.x1 >> 4) - (b.x0 >> 4) + 1) * ((b.y1 >> 4) - (b.y0 >> 4) + 1);
                 faces |= 1u << f;
+                b1 = b;
             }
         }
         big = cover > BP_MAX_COVER;
@@ -376,9 +378,9 @@ __global__ void __launch_bounds__(256) bp_bin_kernel(CellsView g, const float *_
     while (faces) {
         const int f = __ffs(faces) - 1;
         faces &= faces - 1u;
-        QBox b;
+        QBox b = b1;
         bool cl;
-        if (!cell_face_qbox<DIM>(p, n, f, P, &b, &cl)) continue;
+        if (nfaces > 1 && !cell_face_qbox<DIM>(p, n, f, P, &b, &cl)) continue;
         const int4 e = make_int4((int)c, b.x0 | (b.x1 << 16), b.y0 | (b.y1 << 16), 0);
         if (!FILL && rec) rec[c] = make_int4(e.y, e.z, f | (nfaces << 8), 0);
         for (int by = b.y0 >> 4; by <= (b.y1 >> 4); ++by)
