@@ -603,3 +603,32 @@ for k, (d, s) in enumerate(pairs):
         nd = A0.shape[0]
         compare_matrices(A1, A0, a0[:nd], a0[nd:])
         assert abs(A1.sum() - A0.sum()) <= 1e-13 * A0.sum()
+
+
+def test_cell_alignment_dispatch(gpu):
+    """Device-resident vertex soups at every alignment: 32-byte aligned records take the 256-bit loads of the clip
+    kernel, 16-byte aligned ones the 128-bit loads, 8-byte aligned ones the general kernel -- the matrices of the first
+    two are the same bits, the third agrees within the parity bar."""
+    import torch
+    dst, src = grids.lonlat_grid(90, 45), grids.healpix_grid(32, "ring")
+    ref = Regridder(dst, src)
+    A0 = ref.intersections.tocsc()
+
+    def on_device(g, shift_doubles):
+        flat = torch.zeros(g.verts.size + 8, dtype=torch.float64, device="cuda")
+        assert flat.data_ptr() % 32 == 0
+        view = flat[shift_doubles:shift_doubles + g.verts.size].view(g.verts.shape)
+        view.copy_(torch.from_numpy(g.verts))
+        assert view.data_ptr() % 32 == (8 * shift_doubles) % 32
+        return grids.Grid(view, g.manifold), flat
+
+    for shift, exact in ((0, True), (2, True), (1, False)):
+        gd, keep_d = on_device(dst, shift)
+        gs, keep_s = on_device(src, shift)
+        R = Regridder(gd, gs)
+        A = R.intersections.tocsc()
+        if exact:
+            assert (A != A0).nnz == 0, shift
+        else:
+            compare_matrices(A, A0, ref.dst_areas, ref.src_areas)
+        assert np.array_equal(R.dst_areas, ref.dst_areas) and np.array_equal(R.src_areas, ref.src_areas)
